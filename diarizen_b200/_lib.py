@@ -1,0 +1,125 @@
+"""ctypes binding of libdiarizen_b200.so (include/diarizen_b200.h).  No torch types cross this boundary:
+tensors are passed as raw device pointers.  The library is built in-tree by `diarizen_b200/build.py`;
+if it is missing the import fails loudly - there is no Python/CPU fallback for any compute entry point."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiarizen_b200.so")
+
+DZ_MAX_LAYERS = 32
+DZ_MAX_HEADS = 16
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("npass", C.c_int32), ("batches", C.c_int32),
+        ("groups", C.c_int32),
+        ("a", C.c_void_p),
+        ("a_plane", C.c_int64), ("a_bstride", C.c_int64), ("a_gstride", C.c_int64), ("a_rstride", C.c_int64),
+        ("a_kinner", C.c_int32), ("_pad0", C.c_int32),
+        ("a_kouter", C.c_int64), ("a_rows_alloc", C.c_int64),
+        ("b", C.c_void_p),
+        ("b_plane", C.c_int64), ("b_gstride", C.c_int64),
+        ("ldb", C.c_int32), ("act", C.c_int32),
+        ("bias", C.c_void_p),
+        ("alpha", C.c_float),
+        ("group_cols", C.c_int32), ("out_row_off", C.c_int32), ("ldr", C.c_int32),
+        ("residual", C.c_void_p),
+        ("res_bstride", C.c_int64),
+        ("out_f32", C.c_void_p),
+        ("of_bstride", C.c_int64),
+        ("ldo", C.c_int32), ("ldob", C.c_int32),
+        ("out_bf", C.c_void_p),
+        ("ob_plane", C.c_int64), ("ob_bstride", C.c_int64),
+        ("out_planes", C.c_int32), ("zero_pad_to", C.c_int32),
+        ("out_t", C.c_void_p),
+        ("ot_plane", C.c_int64), ("ot_bstride", C.c_int64),
+        ("ldt", C.c_int32), ("tr_col0", C.c_int32), ("seq_len", C.c_int32), ("_pad1", C.c_int32),
+    ]
+
+    @classmethod
+    def default(cls) -> "GemmDesc":
+        d = cls()
+        d.npass = 1
+        d.batches = 1
+        d.groups = 1
+        d.alpha = 1.0
+        d.out_planes = 1
+        d.seq_len = 1
+        return d
+
+
+class SegArchC(C.Structure):
+    _fields_ = [
+        ("large", C.c_int32),
+        ("conv_channels", C.c_int32 * 7),
+        ("embed_dim", C.c_int32), ("total_heads", C.c_int32), ("num_layers", C.c_int32),
+        ("num_heads", C.c_int32 * DZ_MAX_LAYERS),
+        ("head_index", (C.c_int32 * DZ_MAX_HEADS) * DZ_MAX_LAYERS),
+        ("ffn", C.c_int32 * DZ_MAX_LAYERS),
+        ("head_dim_model", C.c_int32), ("head_ffn", C.c_int32), ("head_heads", C.c_int32),
+        ("head_layers", C.c_int32), ("head_kernel", C.c_int32), ("num_classes", C.c_int32),
+    ]
+
+
+class DzError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m diarizen_b200.build` (nvcc, sm_100a). "
+            "diarizen_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.dz_last_error.restype = C.c_char_p
+    L.dz_abi_version.restype = C.c_int
+    L.dz_relpos_bucket.restype = C.c_int
+    L.dz_relpos_bucket.argtypes = [C.c_int]
+    L.dz_gemm.restype = C.c_int
+    L.dz_gemm.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_int, C.c_void_p]
+    L.dz_layernorm.restype = C.c_int
+    L.dz_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                               C.c_int, C.c_int, C.c_void_p]
+    L.dz_seg_create.restype = C.c_void_p
+    L.dz_seg_create.argtypes = [C.POINTER(SegArchC), C.c_int, C.c_int, C.c_int]
+    L.dz_seg_destroy.restype = None
+    L.dz_seg_destroy.argtypes = [C.c_void_p]
+    L.dz_seg_set_param.restype = C.c_int
+    L.dz_seg_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.dz_seg_finalize.restype = C.c_int
+    L.dz_seg_finalize.argtypes = [C.c_void_p]
+    L.dz_seg_num_frames.restype = C.c_int
+    L.dz_seg_num_frames.argtypes = [C.c_void_p, C.c_int]
+    L.dz_seg_forward.restype = C.c_int
+    L.dz_seg_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dz_seg_forward_host.restype = C.c_int
+    L.dz_seg_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.dz_seg_tap.restype = C.c_int64
+    L.dz_seg_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.dz_seg_last_launches.restype = C.c_int
+    L.dz_seg_last_launches.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc < 0:
+        raise DzError(lib().dz_last_error().decode("utf-8", "replace") + f" (code {rc})")
+
+
+EXPORTS = [
+    "dz_last_error", "dz_abi_version", "dz_gemm", "dz_layernorm",
+    "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
+    "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
+]

@@ -1,0 +1,121 @@
+/* diarizen_b200 C ABI  (libdiarizen_b200.so, sm_100a only)
+ *
+ * The reference (BUTSpeechFIT/DiariZen) has no FFI of its own: its hot path is Python calling PyTorch
+ * (SURVEY.md 8b).  The seam this library sits behind is therefore the three device-side callables of
+ * `DiariZenPipeline.__call__` (reference: diarizen/pipelines/inference.py:121-192):
+ *
+ *   dz_seg_*    replaces  self._segmentation.model(chunks.to(device))          pyannote-audio/pyannote/audio/core/inference.py:213-226
+ *                          = Model.forward                                       diarizen/models/eend/model_wavlm_conformer.py:238-264
+ *                          + Powerset.to_multilabel (hard)                       pyannote-audio/pyannote/audio/utils/powerset.py:103-128
+ *   dz_emb_*    replaces  self._embedding(waveform_batch, masks=mask_batch)    pyannote-audio/pyannote/audio/pipelines/speaker_verification.py:693-705
+ *                          = WeSpeakerResNet34.forward                           pyannote-audio/pyannote/audio/models/embedding/wespeaker/__init__.py:190-204
+ *   dz_post_* / dz_cluster_*  replace the numpy/scipy stages                     pyannote-audio/pyannote/audio/pipelines/{clustering,speaker_diarization}.py,
+ *                                                                                pipelines/utils/diarization.py, core/inference.py:543-666
+ *
+ * Conventions: plain C, no torch types.  Every pointer named *_dev is a device pointer on the current
+ * CUDA device; `stream` is a cudaStream_t passed as void* (NULL = default stream).  Functions return 0 on
+ * success and a negative code on failure; dz_last_error() returns a thread-local message.  Nothing in
+ * here falls back to the CPU: on a machine without an sm_100 GPU the compute entry points fail.
+ * Ownership: the caller owns every buffer it passes; handles own their weights and workspace.
+ */
+#ifndef DIARIZEN_B200_H_
+#define DIARIZEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DZ_OK 0
+#define DZ_ERR_INVALID (-1)
+#define DZ_ERR_CUDA (-2)
+#define DZ_ERR_STATE (-3)
+
+const char* dz_last_error(void);
+int dz_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM descriptor: C = epilogue(A * B^T) over bf16 hi/lo planes (see csrc/gemm.h for the A addressing
+ * model that turns conv1d / grouped conv into GEMMs without an im2col copy).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dz_gemm_desc {
+  int32_t M, N, K, npass, batches, groups;
+  const void* a; /* bf16 */
+  int64_t a_plane, a_bstride, a_gstride, a_rstride;
+  int32_t a_kinner, _pad0;
+  int64_t a_kouter, a_rows_alloc;
+  const void* b; /* bf16 [groups][N][ldb] */
+  int64_t b_plane, b_gstride;
+  int32_t ldb, act;
+  const float* bias;
+  float alpha;
+  int32_t group_cols, out_row_off, ldr;
+  const float* residual;
+  int64_t res_bstride;
+  float* out_f32;
+  int64_t of_bstride;
+  int32_t ldo, ldob;
+  void* out_bf; /* bf16 */
+  int64_t ob_plane, ob_bstride;
+  int32_t out_planes, zero_pad_to;
+  void* out_t; /* bf16 */
+  int64_t ot_plane, ot_bstride;
+  int32_t ldt, tr_col0, seq_len, _pad1;
+} dz_gemm_desc;
+
+/* impl: 0 = tcgen05 tensor-core kernel, 1 = CUDA-core checker kernel.  force_bn: 0 auto, or 64/128/256. */
+int dz_gemm(const dz_gemm_desc* d, int impl, int force_bn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element / row kernels of the segmentation path (unit-test surface; the engine calls the same code).
+ * ---------------------------------------------------------------------------------------------- */
+/* y = act(LayerNorm(x * prescale) * gamma + beta) over the last dim C of x[rows][ldx] (eps 1e-5).
+ * Outputs (each optional): fp32 y_f32[rows][ldy]; bf16 planes y_bf[planes][rows][ldb] (pad columns
+ * [C, ldb) zeroed).  mix (optional): mix[rows][ldx] = (mix_init ? 0 : mix) + mix_w * (mix_src==1 ? x : y). */
+int dz_layernorm(const float* x_dev, int64_t rows, int C, int ldx, const float* prescale_dev, const float* gamma_dev,
+                 const float* beta_dev, int act, float* y_f32_dev, int ldy, void* y_bf_dev, int64_t bf_plane,
+                 int ldb, int planes, float* mix_dev, float mix_w, int mix_src, int mix_init, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segmentation engine
+ * ---------------------------------------------------------------------------------------------- */
+#define DZ_MAX_LAYERS 32
+#define DZ_MAX_HEADS 16
+
+typedef struct dz_seg_arch {
+  int32_t large;            /* 1: layer-norm extractor, pre-norm encoder, waveform normalisation */
+  int32_t conv_channels[7];
+  int32_t embed_dim, total_heads, num_layers;
+  int32_t num_heads[DZ_MAX_LAYERS];                 /* remaining heads per layer (0 = no attention) */
+  int32_t head_index[DZ_MAX_LAYERS][DZ_MAX_HEADS];  /* which of the total heads remain */
+  int32_t ffn[DZ_MAX_LAYERS];                       /* 0 = no feed-forward */
+  int32_t head_dim_model, head_ffn, head_heads, head_layers, head_kernel, num_classes;
+} dz_seg_arch;
+
+typedef struct dz_seg dz_seg;
+
+/* precision: 1 = bf16 tensor-core passes, 3 = bf16x3 split (fp32-class).  gemm_impl: 0 tcgen05, 1 CUDA-core.
+ * attn_impl: 0 tcgen05, 1 CUDA-core. */
+dz_seg* dz_seg_create(const dz_seg_arch* arch, int precision, int gemm_impl, int attn_impl);
+void dz_seg_destroy(dz_seg* s);
+/* Parameters are passed by their reference state_dict name (fp32, host memory, C-contiguous). */
+int dz_seg_set_param(dz_seg* s, const char* name, const float* host_data, int64_t numel);
+/* Folds weight-norm / batch-norm / q-scaling, pads irregular widths, splits to bf16 planes, uploads. */
+int dz_seg_finalize(dz_seg* s);
+/* Number of output frames for windows of `num_samples` samples (reference: model_wavlm_conformer.py:98-124). */
+int dz_seg_num_frames(const dz_seg* s, int num_samples);
+/* wav_dev: [B][N] fp32.  logp_dev: [B][T][num_classes] fp32 log-probabilities (may be NULL).
+ * multilabel_dev: [B][T][4] uint8 hard powerset decoding (may be NULL). */
+int dz_seg_forward(dz_seg* s, const float* wav_dev, int B, int N, float* logp_dev, uint8_t* multilabel_dev, void* stream);
+/* Same call with HOST buffers: pinned staging, H2D, forward, D2H inside (the end-to-end path). */
+int dz_seg_forward_host(dz_seg* s, const float* wav_host, int B, int N, float* logp_host, uint8_t* multilabel_host);
+/* Debug tap: copy a named intermediate of the last forward (fp32) into dst_dev; returns element count or <0. */
+int64_t dz_seg_tap(dz_seg* s, const char* name, float* dst_dev, int64_t capacity);
+/* Kernel launches issued by the last dz_seg_forward call. */
+int dz_seg_last_launches(const dz_seg* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIARIZEN_B200_H_ */

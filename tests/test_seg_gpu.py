@@ -1,0 +1,60 @@
+"""Segmentation forward on the GPU vs the fp32 torch oracle (oracle/seg_oracle.py, pinned against the
+reference modules).  Tolerances on log-probabilities follow BASELINE.json north_star: 1e-3 for the
+fp32-class path (bf16x3), 1e-2 for the bf16 path."""
+import pytest
+import torch
+
+from diarizen_b200.archs import get_arch, init_state_dict
+from oracle.seg_oracle import seg_forward, to_multilabel
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name, B, N, precision, gemm_impl, attn_impl, seed=1):
+    from diarizen_b200.segmentation import SegmentationModel
+    a = get_arch(name)
+    sd = init_state_dict(a, seed)
+    g = torch.Generator().manual_seed(1234)
+    wav = 0.1 * torch.randn(B, N, generator=g)
+    ref = seg_forward(a, sd, wav)
+    m = SegmentationModel(a, sd, precision=precision, gemm_impl=gemm_impl, attn_impl=attn_impl)
+    logp, ml = m.hard(wav.unsqueeze(1))
+    torch.cuda.synchronize()
+    return ref, logp.cpu(), ml.cpu(), m
+
+
+@pytest.mark.parametrize("name", ["tiny_base", "tiny_large"])
+@pytest.mark.parametrize("gemm_impl", ["simt", "tc"])
+def test_tiny_fp32_class(name, gemm_impl):
+    ref, logp, ml, _ = _run(name, 3, 16000, "bf16x3", gemm_impl, "simt")
+    assert logp.shape == ref.shape
+    err = (logp - ref).abs().max().item()
+    assert err < 1e-3, f"max |dlogp| = {err:.3e}"
+    # hard decisions agree wherever the oracle's top-2 margin exceeds the tolerance
+    top2 = ref.topk(2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2e-3
+    assert (ml[safe].float() == to_multilabel(ref)[safe]).all()
+
+
+@pytest.mark.parametrize("name", ["tiny_base", "tiny_large"])
+def test_tiny_bf16(name):
+    ref, logp, ml, _ = _run(name, 3, 16000, "bf16", "tc", "simt")
+    err = (logp - ref).abs().max().item()
+    assert err < 1e-2, f"max |dlogp| = {err:.3e}"
+
+
+@pytest.mark.parametrize("name,N,tol", [("wavlm_base_s80_md", 80000, 1e-3), ("wavlm_large_s80_md", 48000, 1e-3)])
+def test_s80_fp32_class(name, N, tol):
+    ref, logp, ml, _ = _run(name, 2, N, "bf16x3", "tc", "simt")
+    err = (logp - ref).abs().max().item()
+    assert err < tol, f"max |dlogp| = {err:.3e}"
+
+
+def test_host_entry_matches_device_entry():
+    from diarizen_b200.segmentation import SegmentationModel
+    m = SegmentationModel.random_init("tiny_base", seed=3, precision="bf16x3", attn_impl="simt")
+    wav = 0.1 * torch.randn(2, 1, 16000)
+    l1, m1 = m.hard(wav)
+    l2, m2 = m.forward_host(wav)
+    assert torch.equal(l1.cpu(), l2) and torch.equal(m1.cpu(), m2)
+    assert m.last_launches > 0
