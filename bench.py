@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the DiariZen inference hot path on B200 (contract: see the task statement).
+
+Default workload (N=1): BASELINE.json configs[1] - WavLM-base-s80 segmentation forward, 5 s / 16 kHz windows,
+batch 256 per GPU, synthetic audio, seeded random-init weights.  One "step" = one forward over one batch.
+Metric = audio-seconds of window audio processed per wall second (RTF^-1), whole job (all ranks).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference         # the reference algorithm on the host cores (oracle port)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SR = 16000
+METRIC = "audio-sec/s (RTF^-1)"
+
+
+def synth_wav(B: int, N: int, seed: int = 1234) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return (0.1 * torch.randn(B, N, generator=g)).clamp_(-1.0, 1.0)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(arch_name: str, N: int, windows: int, chunk: int, repeats: int = 1):
+    """The reference algorithm (oracle port, fp32 torch on the host cores) on a bounded sample."""
+    from diarizen_b200.archs import get_arch, init_state_dict
+    from oracle.seg_oracle import seg_forward
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a = get_arch(arch_name)
+    sd = init_state_dict(a, 0)
+    wav = synth_wav(windows, N)
+    seg_forward(a, sd, wav[:min(2, windows)])  # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for i in range(0, windows, chunk):
+            seg_forward(a, sd, wav[i:i + chunk])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return windows * N / SR / best, cores, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = int(args.seconds * SR)
+    per_step = args.ref_windows
+    cores = os.cpu_count() or 1
+    from diarizen_b200.archs import get_arch, init_state_dict
+    from oracle.seg_oracle import seg_forward
+    torch.set_num_threads(cores)
+    a = get_arch(args.arch)
+    sd = init_state_dict(a, 0)
+    wav = synth_wav(per_step, N)
+    for _ in range(args.warmup):
+        seg_forward(a, sd, wav[:max(1, per_step // 4)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        seg_forward(a, sd, wav)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step * N / SR / dt
+    sample = f"{per_step} windows x {args.seconds:g} s per step ({args.steps} steps), fp32 torch oracle port of Model.forward"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "arch": args.arch, "window_s": args.seconds, "windows_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_name(args):
+    return f"{args.arch} segmentation forward, {args.seconds:g} s / 16 kHz windows, batch {args.batch} per GPU (BASELINE.json configs[1])"
+
+
+def classify(step_name: str) -> str:
+    n = step_name
+    if n.endswith("_attn"):
+        return "attention"
+    if "_ln" in n or n in ("fp_ln", "tr_ln", "head_ln"):
+        return "layernorm"
+    if n.startswith("conv0"):
+        return "conv0"
+    if n in ("wave_stats", "pc_stage", "mix_bf", "mix_last", "classifier") or n.endswith("_mix") or n.endswith("_gate") or n.endswith("_dwconv"):
+        return "elementwise"
+    return "gemm"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="wavlm_base_s80_md")
+    ap.add_argument("--seconds", type=float, default=5.0)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--attn", default=os.environ.get("DZ_ATTN", "simt"), choices=["tc", "simt"])
+    ap.add_argument("--ref-windows", type=int, default=16)
+    ap.add_argument("--cpu-windows", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (sm_100a); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from diarizen_b200.segmentation import SegmentationModel
+    N = int(args.seconds * SR)
+    B = args.batch
+    model = SegmentationModel.random_init(args.arch, seed=0, precision=args.precision, attn_impl=args.attn)
+    wav_host = synth_wav(B, N, seed=1234 + rank).pin_memory()
+    wav_dev = wav_host.cuda()
+    T = model.num_frames(N)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        model.hard(wav_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        model.hard(wav_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.last_launches * args.steps
+    # ---- end to end through the host entry point (pinned host buffers, H2D + D2H inside) ----
+    for _ in range(2):
+        model.forward_host(wav_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.forward_host(wav_host)
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    audio_per_step = world * B * args.seconds
+
+    if rank == 0:
+        peaks = measured_peaks()
+        prof = model.profile(wav_dev)
+        prof = model.profile(wav_dev)
+        classes = {}
+        for name, pms, fl, by in prof:
+            c = classes.setdefault(classify(name), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            c["ms"] += pms; c["flops"] += fl; c["bytes"] += by; c["n"] += 1
+        total_ms = sum(c["ms"] for c in classes.values())
+        dom = max(classes, key=lambda k: classes[k]["ms"])
+        d = classes[dom]
+        npass = 3 if args.precision == "bf16x3" else 1
+        if dom in ("gemm", "attention"):
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel" if dom == "gemm" else "attention", "achieved": ach,
+                    "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                    "peak_source": peaks["src"] + " (sustained bf16)", "launches_per_step": d["n"],
+                    "share_of_step": d["ms"] / total_ms, "tensor_passes": npass}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "launches_per_step": d["n"],
+                    "share_of_step": d["ms"] / total_ms}
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tr = json.load(f)
+            roof["traffic"] = tr.get(roof["kernel"])
+        except Exception:
+            pass
+        breakdown = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4),
+                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
+                         "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
+                     for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+        cpu = None
+        if not args.no_cpu_baseline:
+            rate, cores, secs = cpu_port_rate(args.arch, N, args.cpu_windows, 16)
+            cpu = {"value": rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_windows} windows x {args.seconds:g} s, fp32 torch oracle port of Model.forward, {secs:.1f} s of CPU work"}
+        out = {
+            "metric": METRIC, "value": audio_per_step * args.steps / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if npass == 1 else "bf16x3 (fp32-class)", "data": "synthetic",
+            "config": {"workload": workload_name(args), "arch": args.arch, "window_s": args.seconds, "batch_per_gpu": B,
+                       "frames_per_window": T, "parallelism": f"dp{world} (windows sharded, no data-path collective)",
+                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                       "attention_impl": args.attn},
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "e2e": {"value": audio_per_step * args.steps / (ms_e2e * 1e-3), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": B * N * 4, "d2h_bytes_per_step": B * T * (model.arch.num_classes * 4 + 4),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "breakdown": breakdown,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

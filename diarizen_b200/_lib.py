@@ -109,6 +109,12 @@ def lib() -> C.CDLL:
     L.dz_seg_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
     L.dz_seg_last_launches.restype = C.c_int
     L.dz_seg_last_launches.argtypes = [C.c_void_p]
+    L.dz_seg_num_steps.restype = C.c_int
+    L.dz_seg_num_steps.argtypes = [C.c_void_p]
+    L.dz_seg_step_info.restype = C.c_int
+    L.dz_seg_step_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.dz_seg_profile.restype = C.c_int
+    L.dz_seg_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -122,4 +128,5 @@ EXPORTS = [
     "dz_last_error", "dz_abi_version", "dz_gemm", "dz_layernorm",
     "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
     "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
+    "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",
 ]

@@ -59,7 +59,7 @@ struct Planes {  // activation planes view
 };
 
 typedef std::function<cudaError_t(cudaStream_t)> StepFn;
-struct Step { std::string name; StepFn fn; };
+struct Step { std::string name; StepFn fn; double flops = 0.0; double bytes = 0.0; };
 struct Tap { int step; const float* f32; const bf16* bf; long long bf_plane; long long rows; int C; int ld; };
 
 }  // namespace dz
@@ -412,7 +412,7 @@ struct Planner {
     Planes p; p.p = m->as<bf16>(); p.plane = (long long)elems_per_plane;
     return p;
   }
-  void step(const std::string& name, StepFn fn) { s->steps.push_back({name, fn}); }
+  void step(const std::string& name, StepFn fn, double flops = 0.0, double bytes = 0.0) { s->steps.push_back({name, fn, flops, bytes}); }
   void tap_f32(const std::string& name, const float* p, long long rows, int C, int ld) {
     s->taps[name] = Tap{(int)s->steps.size(), p, nullptr, 0, rows, C, ld};
   }
@@ -422,14 +422,15 @@ struct Planner {
   void gemm(const std::string& name, GemmDesc d) {
     d.npass = npass;
     d.out_planes = P;
+    const double flops = 2.0 * d.M * (double)d.N * d.K * d.batches * d.groups;  // algorithmic (one pass, valid dims)
     if (s->gemm_impl == 1) {
-      step(name, [d](cudaStream_t st) { return gemm_simt_launch(d, st); });
+      step(name, [d](cudaStream_t st) { return gemm_simt_launch(d, st); }, flops);
       return;
     }
     GemmPlan* p = gemm_plan_create(d, 0);
     if (!p) { if (!err) { err = DZ_ERR_CUDA; msg = "gemm plan '" + name + "': " + gemm_last_error(); } return; }
     s->plans.push_back(p);
-    step(name, [p](cudaStream_t st) { return gemm_plan_launch(p, st); });
+    step(name, [p](cudaStream_t st) { return gemm_plan_launch(p, st); }, flops);
   }
   // plain linear: A planes [rows][lda] x W -> epilogue
   GemmDesc linear(Planes A, int lda, long long rows, const Weight& W) {
@@ -440,7 +441,14 @@ struct Planner {
     d.bias = W.bias.as<float>();
     return d;
   }
-  void layernorm(const std::string& name, LnArgs a) { step(name, [a](cudaStream_t st) { return launch_layernorm(a, st); }); }
+  void layernorm(const std::string& name, LnArgs a) {
+    // algorithmic HBM bytes: read the row once, write each requested output once (mix: read-modify-write)
+    double per = 4.0;
+    if (a.y_f32) per += 4.0;
+    if (a.y_bf) per += 2.0 * a.planes;
+    if (a.mix) per += a.mix_init ? 4.0 : 8.0;
+    step(name, [a](cudaStream_t st) { return launch_layernorm(a, st); }, 0.0, per * (double)a.rows * a.C);
+  }
 };
 
 static int plan_impl(dz_seg* s, int B, int N) {
@@ -486,7 +494,8 @@ static int plan_impl(dz_seg* s, int B, int N) {
       p.step("conv0_moments", [s, B, N, T0, mom](cudaStream_t st) { return launch_conv0_moments(s->cur_wav, B, N, T0, mom, st); });
       p.step("conv0_gn_coef", [=](cudaStream_t st) { return launch_conv0_gn_coef(mom, w0, g0, b0, B, C0, T0, coef, st); });
     }
-    p.step("conv0", [s, c, B, large](cudaStream_t st) { Conv0Args cc = c; cc.wav = s->cur_wav; return launch_conv0(cc, B, large, st); });
+    p.step("conv0", [s, c, B, large](cudaStream_t st) { Conv0Args cc = c; cc.wav = s->cur_wav; return launch_conv0(cc, B, large, st); },
+           0.0, (double)B * N * 4.0 + (double)B * Tl[0] * Cp[0] * 2.0 * P);
     p.tap_bf("conv0", act[0], (long long)B * Tl[0], a.conv_channels[0], Cp[0]);
   }
   float* feats = convf;  // [B*T][Cp[6]] fp32 after the last conv
@@ -600,7 +609,8 @@ static int plan_impl(dz_seg* s, int B, int N) {
     at.vt = vt.p; at.vt_plane = vt.plane; at.ldvt = Tp; at.planes = P; at.bias_tab = tab; at.gate = gatep;
     at.out = ctx.p; at.out_plane = ctx.plane; at.ldo = h * 64; at.out_planes = P;
     const int impl = s->attn_impl;
-    p.step(nm + "_attn", [at, B, impl](cudaStream_t st) { return impl == 0 ? launch_attention_tc(at, B, st) : launch_attention_simt(at, B, st); });
+    p.step(nm + "_attn", [at, B, impl](cudaStream_t st) { return impl == 0 ? launch_attention_tc(at, B, st) : launch_attention_simt(at, B, st); },
+           4.0 * (double)T * T * 64 * h * B);
     p.tap_bf(nm + "_ctx", ctx, R, h * 64, h * 64);
     GemmDesc o = p.linear(ctx, h * 64, R, Wo);
     o.residual = resid; o.ldr = ldres; o.out_f32 = resid; o.ldo = ldres;
@@ -822,19 +832,27 @@ int dz_seg_forward_host(dz_seg* s, const float* wav_host, int B, int N, float* l
   if (e == cudaSuccess && s->pin_logp_n < nl) { if (s->pin_logp) cudaFreeHost(s->pin_logp); e = cudaMallocHost((void**)&s->pin_logp, nl * 4); s->pin_logp_n = nl; if (e == cudaSuccess) e = s->dev_logp.alloc(nl * 4, false); }
   if (e == cudaSuccess && s->pin_ml_n < nm) { if (s->pin_ml) cudaFreeHost(s->pin_ml); e = cudaMallocHost((void**)&s->pin_ml, nm); s->pin_ml_n = nm; if (e == cudaSuccess) e = s->dev_ml.alloc(nm, false); }
   if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("staging allocation failed: ") + cudaGetErrorString(e));
-  memcpy(s->pin_wav, wav_host, nw * 4);
+  // caller-pinned buffers are copied from/to directly; pageable ones go through the pinned staging area
+  auto is_pinned = [](const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool pin_in = is_pinned(wav_host);
+  const bool pin_l = logp_host && is_pinned(logp_host), pin_m = multilabel_host && is_pinned(multilabel_host);
+  if (!pin_in) memcpy(s->pin_wav, wav_host, nw * 4);
   cudaStream_t st = s->own_stream;
-  e = cudaMemcpyAsync(s->dev_wav.p, s->pin_wav, nw * 4, cudaMemcpyHostToDevice, st);
+  e = cudaMemcpyAsync(s->dev_wav.p, pin_in ? wav_host : s->pin_wav, nw * 4, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("H2D failed: ") + cudaGetErrorString(e));
   int r = seg_run(s, s->dev_wav.as<float>(), B, N, logp_host ? s->dev_logp.as<float>() : nullptr,
                   multilabel_host ? s->dev_ml.as<uint8_t>() : nullptr, st, -1);
   if (r != DZ_OK) return r;
-  if (logp_host) cudaMemcpyAsync(s->pin_logp, s->dev_logp.p, nl * 4, cudaMemcpyDeviceToHost, st);
-  if (multilabel_host) cudaMemcpyAsync(s->pin_ml, s->dev_ml.p, nm, cudaMemcpyDeviceToHost, st);
+  if (logp_host) cudaMemcpyAsync(pin_l ? logp_host : s->pin_logp, s->dev_logp.p, nl * 4, cudaMemcpyDeviceToHost, st);
+  if (multilabel_host) cudaMemcpyAsync(pin_m ? multilabel_host : s->pin_ml, s->dev_ml.p, nm, cudaMemcpyDeviceToHost, st);
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("forward failed: ") + cudaGetErrorString(e));
-  if (logp_host) memcpy(logp_host, s->pin_logp, nl * 4);
-  if (multilabel_host) memcpy(multilabel_host, s->pin_ml, nm);
+  if (logp_host && !pin_l) memcpy(logp_host, s->pin_logp, nl * 4);
+  if (multilabel_host && !pin_m) memcpy(multilabel_host, s->pin_ml, nm);
   return DZ_OK;
 }
 
@@ -875,5 +893,38 @@ int64_t dz_seg_tap(dz_seg* s, const char* name, float* dst_dev, int64_t capacity
 }
 
 int dz_seg_last_launches(const dz_seg* s) { return s ? s->last_launches : 0; }
+
+int dz_seg_num_steps(const dz_seg* s) { return s ? (int)s->steps.size() : 0; }
+
+int dz_seg_step_info(const dz_seg* s, int i, char* name_buf, int name_cap, double* flops, double* bytes) {
+  if (s && bytes && i >= 0 && i < (int)s->steps.size()) *bytes = s->steps[i].bytes;
+  if (!s || i < 0 || i >= (int)s->steps.size()) return fail(DZ_ERR_INVALID, "bad step index");
+  if (name_buf && name_cap > 0) { strncpy(name_buf, s->steps[i].name.c_str(), name_cap - 1); name_buf[name_cap - 1] = 0; }
+  if (flops) *flops = s->steps[i].flops;
+  return DZ_OK;
+}
+
+int dz_seg_profile(dz_seg* s, const float* wav_dev, int B, int N, float* ms_out, int cap, void* stream) {
+  if (!s || !wav_dev || !ms_out) return fail(DZ_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = seg_run(s, wav_dev, B, N, nullptr, nullptr, st, 0);  // plan only
+  if (r != DZ_OK) return r;
+  const int n = (int)s->steps.size();
+  if (cap < n) return fail(DZ_ERR_INVALID, "ms_out too small");
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  s->cur_wav = wav_dev; s->cur_logp = nullptr; s->cur_ml = nullptr;
+  cudaEventRecord(ev[0], st);
+  for (int i = 0; i < n; ++i) {
+    cudaError_t e = s->steps[i].fn(st);
+    if (e != cudaSuccess) return fail(DZ_ERR_CUDA, "launch '" + s->steps[i].name + "' failed: " + cudaGetErrorString(e));
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("profile failed: ") + cudaGetErrorString(e));
+  for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& ev1 : ev) cudaEventDestroy(ev1);
+  return n;
+}
 
 }  // extern "C"

@@ -105,8 +105,9 @@ class SegmentationModel:
         w = wav_host.to("cpu", torch.float32).contiguous()
         B, N = w.shape
         T = self.num_frames(N)
-        logp = torch.empty((B, T, self.arch.num_classes), dtype=torch.float32)
-        ml = torch.empty((B, T, NUM_SPEAKERS), dtype=torch.uint8)
+        pin = w.is_pinned()
+        logp = torch.empty((B, T, self.arch.num_classes), dtype=torch.float32, pin_memory=pin)
+        ml = torch.empty((B, T, NUM_SPEAKERS), dtype=torch.uint8, pin_memory=pin)
         with torch.cuda.device(self.device):
             _lib.check(self._L.dz_seg_forward_host(self._h, C.c_void_p(w.data_ptr()), B, N,
                                                    C.c_void_p(logp.data_ptr()), C.c_void_p(ml.data_ptr())))
@@ -119,6 +120,25 @@ class SegmentationModel:
             _lib.check(n)
             out = torch.empty(n, device=self.device, dtype=torch.float32)
             _lib.check(self._L.dz_seg_tap(self._h, name.encode(), C.c_void_p(out.data_ptr()), n))
+        return out
+
+    def profile(self, waveforms: torch.Tensor):
+        """Per-launch device times of one forward: list of (name, ms, algorithmic_flops, algorithmic_bytes)."""
+        import ctypes as C
+        w = self._prep(waveforms)
+        B, N = w.shape
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            ms = (C.c_float * 4096)()
+            n = self._L.dz_seg_profile(self._h, C.c_void_p(w.data_ptr()), B, N, ms, 4096, C.c_void_p(st))
+            _lib.check(n)
+            out = []
+            buf = C.create_string_buffer(128)
+            fl, by = C.c_double(), C.c_double()
+            for i in range(n):
+                _lib.check(self._L.dz_seg_step_info(self._h, i, buf, 128, C.byref(fl), C.byref(by)))
+                out.append((buf.value.decode(), float(ms[i]), float(fl.value), float(by.value)))
+        self._keep = w
         return out
 
     @property

@@ -114,6 +114,13 @@ int dz_seg_forward_host(dz_seg* s, const float* wav_host, int B, int N, float* l
 int64_t dz_seg_tap(dz_seg* s, const char* name, float* dst_dev, int64_t capacity);
 /* Kernel launches issued by the last dz_seg_forward call. */
 int dz_seg_last_launches(const dz_seg* s);
+/* Launch list of the current plan: name and algorithmic FLOPs (2*M*N*K for GEMMs, 4*T*T*64*h*B for attention,
+ * 0 for bandwidth kernels) and algorithmic HBM bytes (bandwidth kernels) of step i. */
+int dz_seg_num_steps(const dz_seg* s);
+int dz_seg_step_info(const dz_seg* s, int i, char* name_buf, int name_cap, double* flops, double* bytes);
+/* Runs one forward with a CUDA event pair around every launch; ms_out[i] = device time of step i.
+ * Returns the number of steps (diagnostic path: events serialise nothing but add ~us per launch). */
+int dz_seg_profile(dz_seg* s, const float* wav_dev, int B, int N, float* ms_out, int cap, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _tol(npass):
-    return 5e-4 if npass == 1 else 3e-5
+    return 5e-4 if npass == 1 else 8e-5
 
 
 def _check(name, got, ref, npass):
@@ -20,7 +20,7 @@ def _check(name, got, ref, npass):
     assert err < _tol(npass), f"{name}: rel err {err:.3e}"
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
 @pytest.mark.parametrize("npass", [1, 3])
 @pytest.mark.parametrize("M,N,K,bn", [(300, 200, 136, 0), (128, 64, 64, 64), (257, 666, 768, 128), (513, 1092, 1024, 256),
                                      (96, 11, 256, 0), (1000, 384, 53, 0)])
@@ -52,7 +52,7 @@ def test_linear_epilogue(impl, npass, M, N, K, bn):
     assert (out_f[:, N:] == 7.0).all(), "fp32 output must not touch pad columns"
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
 @pytest.mark.parametrize("npass", [1, 3])
 @pytest.mark.parametrize("B,Tin,Cin,Cout,k", [(3, 401, 24, 40, 3), (2, 1000, 153, 224, 3), (2, 300, 90, 161, 2)])
 def test_conv1d_as_strided_gemm(impl, npass, B, Tin, Cin, Cout, k):
@@ -82,7 +82,7 @@ def test_conv1d_as_strided_gemm(impl, npass, B, Tin, Cin, Cout, k):
     _check("conv", out[..., :Cout], ref, npass)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
 @pytest.mark.parametrize("npass", [1, 3])
 @pytest.mark.parametrize("B,T,D", [(2, 49, 128), (2, 249, 768), (1, 300, 1024)])
 def test_grouped_posconv(impl, npass, B, T, D):
@@ -117,7 +117,7 @@ def test_grouped_posconv(impl, npass, B, T, D):
     _check("posconv", res.view(B, T, D), ref, npass)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
 def test_transposed_output(impl):
     """q|k row-major + v^T planes from one projection GEMM."""
     torch.manual_seed(5)
