@@ -92,12 +92,41 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_THREADS = {}
+
+
+def pick_threads(arch_name: str, N: int) -> int:
+    """torch's intra-op pool degrades badly when oversubscribed on many-core hosts: try a few pool sizes on two
+    windows and keep the fastest (that count is what `cores` reports)."""
+    key = (arch_name, N)
+    if key in _THREADS:
+        torch.set_num_threads(_THREADS[key])
+        return _THREADS[key]
+    from diarizen_b200.archs import get_arch, init_state_dict
+    from oracle.seg_oracle import seg_forward
+    ncpu = os.cpu_count() or 1
+    a = get_arch(arch_name)
+    sd = init_state_dict(a, 0)
+    wav = synth_wav(2, N)
+    best, best_t = None, None
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(n)
+        seg_forward(a, sd, wav[:1])
+        t0 = time.perf_counter()
+        seg_forward(a, sd, wav)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    _THREADS[key] = best
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_port_rate(arch_name: str, N: int, windows: int, chunk: int, repeats: int = 1):
     """The reference algorithm (oracle port, fp32 torch on the host cores) on a bounded sample."""
     from diarizen_b200.archs import get_arch, init_state_dict
     from oracle.seg_oracle import seg_forward
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_threads(arch_name, N)
     a = get_arch(arch_name)
     sd = init_state_dict(a, 0)
     wav = synth_wav(windows, N)
@@ -118,10 +147,9 @@ def run_reference(args):
         return
     N = int(args.seconds * SR)
     per_step = args.ref_windows
-    cores = os.cpu_count() or 1
     from diarizen_b200.archs import get_arch, init_state_dict
     from oracle.seg_oracle import seg_forward
-    torch.set_num_threads(cores)
+    cores = pick_threads(args.arch, N)
     a = get_arch(args.arch)
     sd = init_state_dict(a, 0)
     wav = synth_wav(per_step, N)
@@ -170,8 +198,9 @@ def main():
     ap.add_argument("--arch", default="wavlm_base_s80_md")
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
-    ap.add_argument("--attn", default=os.environ.get("DZ_ATTN", "simt"), choices=["tc", "simt"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16x3"])
+    ap.add_argument("--profile-out", default=None, help="write the per-launch table (name, ms, flops, bytes) as JSON")
+    ap.add_argument("--attn", default=os.environ.get("DZ_ATTN", "tc"), choices=["tc", "simt"])
     ap.add_argument("--ref-windows", type=int, default=16)
     ap.add_argument("--cpu-windows", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -244,6 +273,10 @@ def main():
         peaks = measured_peaks()
         prof = model.profile(wav_dev)
         prof = model.profile(wav_dev)
+        if args.profile_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+            with open(args.profile_out, "w") as f:
+                json.dump([{"name": n, "ms": m, "flops": fl, "bytes": by} for n, m, fl, by in prof], f, indent=0)
         classes = {}
         for name, pms, fl, by in prof:
             c = classes.setdefault(classify(name), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
@@ -281,7 +314,9 @@ def main():
         out = {
             "metric": METRIC, "value": audio_per_step * args.steps / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if npass == 1 else "bf16x3 (fp32-class)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "fp16 operands, fp32 accumulate", "bf16": "bf16 operands, fp32 accumulate", "bf16x3": "bf16x3 split (fp32-class)"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": workload_name(args), "arch": args.arch, "window_s": args.seconds, "batch_per_gpu": B,
                        "frames_per_window": T, "parallelism": f"dp{world} (windows sharded, no data-path collective)",
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",

@@ -19,7 +19,7 @@ class GemmDesc(C.Structure):
         ("groups", C.c_int32),
         ("a", C.c_void_p),
         ("a_plane", C.c_int64), ("a_bstride", C.c_int64), ("a_gstride", C.c_int64), ("a_rstride", C.c_int64),
-        ("a_kinner", C.c_int32), ("_pad0", C.c_int32),
+        ("a_kinner", C.c_int32), ("fp16", C.c_int32),
         ("a_kouter", C.c_int64), ("a_rows_alloc", C.c_int64),
         ("b", C.c_void_p),
         ("b_plane", C.c_int64), ("b_gstride", C.c_int64),
@@ -65,6 +65,17 @@ class SegArchC(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("T", C.c_int32), ("nheads", C.c_int32),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("qk_plane", C.c_int64), ("ldqk", C.c_int32), ("q_col", C.c_int32),
+        ("k_col", C.c_int32), ("fp16", C.c_int32),
+        ("vt", C.c_void_p), ("vt_plane", C.c_int64), ("ldvt", C.c_int32), ("planes", C.c_int32),
+        ("bias_tab", C.c_void_p), ("gate", C.c_void_p),
+        ("out", C.c_void_p), ("out_plane", C.c_int64), ("ldo", C.c_int32), ("out_planes", C.c_int32),
+    ]
+
+
 class DzError(RuntimeError):
     pass
 
@@ -90,7 +101,9 @@ def lib() -> C.CDLL:
     L.dz_layernorm.restype = C.c_int
     L.dz_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_float,
-                               C.c_int, C.c_int, C.c_void_p]
+                               C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.dz_attention.restype = C.c_int
+    L.dz_attention.argtypes = [C.POINTER(AttnArgs), C.c_int, C.c_int, C.c_void_p]
     L.dz_seg_create.restype = C.c_void_p
     L.dz_seg_create.argtypes = [C.POINTER(SegArchC), C.c_int, C.c_int, C.c_int]
     L.dz_seg_destroy.restype = None
@@ -125,7 +138,7 @@ def check(rc: int) -> None:
 
 
 EXPORTS = [
-    "dz_last_error", "dz_abi_version", "dz_gemm", "dz_layernorm",
+    "dz_last_error", "dz_abi_version", "dz_gemm", "dz_layernorm", "dz_attention",
     "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
     "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
     "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -114,11 +115,11 @@ DZ_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 accumulate.
-DZ_DEVINL uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+DZ_DEVINL uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, int fp16 = 0) {
   uint32_t d = 0;
-  d |= 1u << 4;          // D format = F32
-  d |= 1u << 7;          // A format = BF16
-  d |= 1u << 10;         // B format = BF16
+  d |= 1u << 4;                    // D format = F32
+  d |= (fp16 ? 0u : 1u) << 7;      // A format: 0 = F16, 1 = BF16
+  d |= (fp16 ? 0u : 1u) << 10;     // B format
   d |= (n >> 3) << 17;   // N
   d |= (m >> 4) << 24;   // M
   return d;
@@ -177,10 +178,22 @@ DZ_DEVINL float apply_act(float x, int act) {
     default: return x;
   }
 }
-// fp32 -> (hi, lo) bf16 planes: hi = rn(x), lo = rn(x - hi); hi + lo carries ~16 mantissa bits.
-DZ_DEVINL void split_bf16(float x, bf16& hi, bf16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// 16-bit operand planes.  The storage type is `bf16` (a 16-bit container); `fp16` selects how the bits are
+// interpreted: 0 = bfloat16 (8-bit mantissa, fp32 range), 1 = IEEE half (11-bit mantissa, saturating at 65504).
+DZ_DEVINL bf16 to16(float x, int fp16) {
+  if (fp16) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(x)));
+  }
+  return __float2bfloat16_rn(x);
+}
+DZ_DEVINL float from16(bf16 h, int fp16) {
+  return fp16 ? __half2float(__ushort_as_half(__bfloat16_as_ushort(h))) : __bfloat162float(h);
+}
+// fp32 -> (hi, lo) planes: hi = rn(x), lo = rn(x - hi); with bf16, hi + lo carries ~16 mantissa bits.
+DZ_DEVINL void split_bf16(float x, bf16& hi, bf16& lo, int fp16) {
+  hi = to16(x, fp16);
+  lo = to16(x - from16(hi, fp16), fp16);
 }
 DZ_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -66,8 +66,8 @@ DZ_DEVINL void gemm_epilogue_chunk(const GemmDesc& d, int b, int g, int m, int n
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           bf16 h0, l0, h1, l1;
-          split_bf16(v[8 * q + 2 * e], h0, l0);
-          split_bf16(v[8 * q + 2 * e + 1], h1, l1);
+          split_bf16(v[8 * q + 2 * e], h0, l0, d.fp16);
+          split_bf16(v[8 * q + 2 * e + 1], h1, l1, d.fp16);
           hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
@@ -80,7 +80,7 @@ DZ_DEVINL void gemm_epilogue_chunk(const GemmDesc& d, int b, int g, int m, int n
         const int c = n0 + j;
         if (c < rm_cols) {
           bf16 h, l;
-          split_bf16(v[j], h, l);
+          split_bf16(v[j], h, l, d.fp16);
           hp[j] = h;
           if (d.out_planes > 1) hp[d.ob_plane + j] = l;
         } else if (c < d.zero_pad_to && d.out_t == nullptr) {
@@ -99,7 +99,7 @@ DZ_DEVINL void gemm_epilogue_chunk(const GemmDesc& d, int b, int g, int m, int n
       const int c = gcol0 + j;
       if (c >= d.tr_col0 && j < nvalid) {
         bf16 h, l;
-        split_bf16(v[j], h, l);
+        split_bf16(v[j], h, l, d.fp16);
         bf16* q = tp + (long long)(c - d.tr_col0) * d.ldt;
         *q = h;
         if (d.out_planes > 1) q[d.ot_plane] = l;

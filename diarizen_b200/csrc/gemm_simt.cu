@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
       float v = 0.f;
       if (k < d.K && m < d.M) {
         const long long off = (long long)m * d.a_rstride + (long long)(k / d.a_kinner) * d.a_kouter + (k % d.a_kinner);
-        v = __bfloat162float(abase[off]);
-        if (two) v += __bfloat162float(abase[d.a_plane + off]);
+        v = from16(abase[off], d.fp16);
+        if (two) v += from16(abase[d.a_plane + off], d.fp16);
       }
       As[kk][rr] = v;
     }
@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
       float v = 0.f;
       if (k < d.K && n < d.N) {
         const long long off = (long long)n * d.ldb + k;
-        v = __bfloat162float(bbase[off]);
-        if (two) v += __bfloat162float(bbase[d.b_plane + off]);
+        v = from16(bbase[off], d.fp16);
+        if (two) v += from16(bbase[d.b_plane + off], d.fp16);
       }
       Bs[kk][nn] = v;
     }

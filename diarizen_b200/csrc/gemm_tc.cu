@@ -100,7 +100,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
     if (lane == 0) {
       const int n_valid = min(BN, d.N - n0);
       const uint32_t umma_n = (uint32_t)((n_valid + 15) & ~15);
-      const uint32_t idesc = umma_idesc_bf16(BM, umma_n);
+      const uint32_t idesc = umma_idesc_bf16(BM, umma_n, d.fp16);
       for (int it = 0; it < iters; ++it) {
         const int s = it % C::NSTAGE;
         const uint32_t ph = (it / C::NSTAGE) & 1;

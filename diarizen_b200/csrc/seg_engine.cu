@@ -68,7 +68,7 @@ using namespace dz;
 
 struct dz_seg {
   dz_seg_arch arch;
-  int precision = 1, planes = 1, gemm_impl = 0, attn_impl = 0;
+  int precision = 1, planes = 1, npass = 1, fp16 = 0, gemm_impl = 0, attn_impl = 0;
   std::map<std::string, std::vector<float>> params;
   bool finalized = false;
 
@@ -99,6 +99,7 @@ struct dz_seg {
   std::vector<Step> steps;
   std::map<std::string, Tap> taps;
   std::vector<GemmPlan*> plans;
+  std::vector<AttnPlan*> aplans;
   std::vector<DevMem*> ws;  // workspace buffers
   DevMem bias_tab;
   const float* cur_wav = nullptr;
@@ -110,6 +111,9 @@ struct dz_seg {
   size_t pin_wav_n = 0, pin_logp_n = 0, pin_ml_n = 0;
   DevMem dev_wav, dev_logp, dev_ml;
   cudaStream_t own_stream = nullptr;
+  cudaEvent_t done_event = nullptr;   // recorded after every run: the workspace is shared across streams
+  cudaStream_t last_stream = nullptr;
+  bool ran = false;
 
   ~dz_seg() {
     clear_plan();
@@ -117,10 +121,13 @@ struct dz_seg {
     if (pin_logp) cudaFreeHost(pin_logp);
     if (pin_ml) cudaFreeHost(pin_ml);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (done_event) cudaEventDestroy(done_event);
   }
   void clear_plan() {
     for (auto* p : plans) gemm_plan_destroy(p);
     plans.clear();
+    for (auto* p : aplans) attention_tc_plan_destroy(p);
+    aplans.clear();
     for (auto* w : ws) delete w;
     ws.clear();
     steps.clear();
@@ -168,6 +175,21 @@ static inline float bf2f(uint16_t h) {
   return x;
 }
 
+static inline uint16_t f2h(float x) {  // fp32 -> IEEE half, round-to-nearest-even, saturating
+  if (x > 65504.f) x = 65504.f;
+  if (x < -65504.f) x = -65504.f;
+  __half h = __float2half_rn(x);  // host-callable conversion (cuda_fp16.h)
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+static inline float h2f(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+static int g_weight_fp16 = 0;  // set by finalize_impl for the duration of the weight build
+
 // w: [groups][N][K] fp32 row-major -> device planes [2][groups][N][ldb]; bias (may be null) -> fp32 padded.
 static cudaError_t make_weight(Weight& W, const float* w, int groups, int N, int K, const float* bias, int nbias) {
   W.N = N; W.K = K; W.groups = groups;
@@ -179,8 +201,8 @@ static cudaError_t make_weight(Weight& W, const float* w, int groups, int N, int
     for (int n = 0; n < N; ++n)
       for (int k = 0; k < K; ++k) {
         const float x = w[((size_t)g * N + n) * K + k];
-        const uint16_t hi = f2bf(x);
-        const uint16_t lo = f2bf(x - bf2f(hi));
+        const uint16_t hi = g_weight_fp16 ? f2h(x) : f2bf(x);
+        const uint16_t lo = g_weight_fp16 ? f2h(x - h2f(hi)) : f2bf(x - bf2f(hi));
         const size_t o = (size_t)g * W.gstride + (size_t)n * W.ldb + k;
         h[o] = hi;
         h[(size_t)W.plane + o] = lo;
@@ -217,6 +239,7 @@ struct Builder {
 
 static int finalize_impl(dz_seg* s) {
   const dz_seg_arch& a = s->arch;
+  g_weight_fp16 = s->fp16;
   Builder b{s};
   const std::string fe = "wavlm_model.feature_extractor.";
   const int D = a.embed_dim, H = a.total_heads;
@@ -422,6 +445,7 @@ struct Planner {
   void gemm(const std::string& name, GemmDesc d) {
     d.npass = npass;
     d.out_planes = P;
+    d.fp16 = s->fp16;
     const double flops = 2.0 * d.M * (double)d.N * d.K * d.batches * d.groups;  // algorithmic (one pass, valid dims)
     if (s->gemm_impl == 1) {
       step(name, [d](cudaStream_t st) { return gemm_simt_launch(d, st); }, flops);
@@ -442,6 +466,7 @@ struct Planner {
     return d;
   }
   void layernorm(const std::string& name, LnArgs a) {
+    a.fp16 = s->fp16;
     // algorithmic HBM bytes: read the row once, write each requested output once (mix: read-modify-write)
     double per = 4.0;
     if (a.y_f32) per += 4.0;
@@ -455,7 +480,8 @@ static int plan_impl(dz_seg* s, int B, int N) {
   s->clear_plan();
   const dz_seg_arch& a = s->arch;
   Planner p{s};
-  p.P = s->planes; p.npass = s->precision;
+  p.P = s->planes; p.npass = s->npass;
+  const int FP = s->fp16;
   const int P = s->planes;
   int Tl[7], Cp[7];
   {
@@ -485,7 +511,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
     if (c.C0p64 > 512) return fail(DZ_ERR_INVALID, "conv0 wider than 512 channels unsupported");
     c.w = s->conv0_w.as<float>(); c.wstats = wstats; c.coef = coef;
     c.gamma = s->conv0_gamma.as<float>(); c.beta = s->conv0_beta.as<float>();
-    c.out = act[0].p; c.out_plane = act[0].plane; c.out_bstride = (long long)Tl[0] * Cp[0]; c.ldo = Cp[0]; c.planes = P;
+    c.out = act[0].p; c.out_plane = act[0].plane; c.out_bstride = (long long)Tl[0] * Cp[0]; c.ldo = Cp[0]; c.planes = P; c.fp16 = FP;
     const float* g0 = s->conv0_gamma.as<float>(); const float* b0 = s->conv0_beta.as<float>(); const float* w0 = s->conv0_w.as<float>();
     const int C0 = c.C0, T0 = Tl[0];
     if (large) {
@@ -561,7 +587,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
   {
     const int Dg = D / 16;
     p.step("pc_stage", [=](cudaStream_t st) {
-      return launch_regroup(xres, R, D, Dp, T, PCR, 64, Dg, 64, stage.p, stage.plane, PCW, P, st);
+      return launch_regroup(xres, R, D, Dp, T, PCR, 64, Dg, 64, stage.p, stage.plane, PCW, P, FP, st);
     });
     const Weight& W = s->pc_w;
     GemmDesc d = gemm_desc_default();
@@ -607,10 +633,18 @@ static int plan_impl(dz_seg* s, int B, int N) {
     AttnArgs at{};
     at.T = T; at.nheads = h; at.q = qk.p; at.k = qk.p; at.qk_plane = qk.plane; at.ldqk = 2 * h * 64; at.q_col = 0; at.k_col = h * 64;
     at.vt = vt.p; at.vt_plane = vt.plane; at.ldvt = Tp; at.planes = P; at.bias_tab = tab; at.gate = gatep;
-    at.out = ctx.p; at.out_plane = ctx.plane; at.ldo = h * 64; at.out_planes = P;
-    const int impl = s->attn_impl;
-    p.step(nm + "_attn", [at, B, impl](cudaStream_t st) { return impl == 0 ? launch_attention_tc(at, B, st) : launch_attention_simt(at, B, st); },
-           4.0 * (double)T * T * 64 * h * B);
+    at.out = ctx.p; at.out_plane = ctx.plane; at.ldo = h * 64; at.out_planes = P; at.fp16 = FP;
+    // the tensor-core attention kernel multiplies the hi planes only; the fp32-class mode uses the CUDA-core kernel
+    const int impl = (s->npass == 3) ? 1 : s->attn_impl;
+    const double aflops = 4.0 * (double)T * T * 64 * h * B;
+    if (impl == 0) {
+      AttnPlan* ap = attention_tc_plan_create(at, B);
+      if (!ap) { if (!p.err) { p.err = DZ_ERR_CUDA; p.msg = "attention plan '" + nm + "': " + gemm_last_error(); } return; }
+      s->aplans.push_back(ap);
+      p.step(nm + "_attn", [ap](cudaStream_t st) { return attention_tc_plan_launch(ap, st); }, aflops);
+    } else {
+      p.step(nm + "_attn", [at, B](cudaStream_t st) { return launch_attention_simt(at, B, st); }, aflops);
+    }
     p.tap_bf(nm + "_ctx", ctx, R, h * 64, h * 64);
     GemmDesc o = p.linear(ctx, h * 64, R, Wo);
     o.residual = resid; o.ldr = ldres; o.out_f32 = resid; o.ldo = ldres;
@@ -635,7 +669,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
         GateArgs g{};
         g.x = xbf.p; g.x_plane = xbf.plane; g.planes = P; g.rows = R; g.ldx = Dp; g.seq_len = T;
         g.wab = L.wab.as<float>(); g.ba = L.ba; g.bb = L.bb; g.gconst = L.gconst.as<float>();
-        g.head_index = L.head_index.as<int>(); g.nheads = h; g.gate = gate;
+        g.head_index = L.head_index.as<int>(); g.nheads = h; g.gate = gate; g.fp16 = FP;
         p.step(nm + "_gate", [g](cudaStream_t st) { return launch_gate(g, st); });
         tab = s->bias_tab.as<float>() + tab_off[l]; gp = gate;
       }
@@ -685,7 +719,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
   // ---------------- conformer head ----------------
   float* hx = p.buf((size_t)R * A * 4 + 256, true)->as<float>();
   float* pw1o = p.buf((size_t)R * 2 * A * 4 + 256, true)->as<float>();
-  p.step("mix_bf", [=](cudaStream_t st) { return launch_regroup(mix, R, D, Dp, 1, 1, 0, D, D, xbf.p, xbf.plane, Dp, P, st); });
+  p.step("mix_bf", [=](cudaStream_t st) { return launch_regroup(mix, R, D, Dp, 1, 1, 0, D, D, xbf.p, xbf.plane, Dp, P, FP, st); });
   {
     GemmDesc d = p.linear(xbf, Dp, R, s->proj_w);
     d.out_f32 = hx; d.ldo = A;
@@ -725,7 +759,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
       DwArgs dw{};
       dw.x = pw1o; dw.ldx = 2 * A; dw.T = T; dw.A = A; dw.ksize = a.head_kernel;
       dw.w = C.dw_w.as<float>(); dw.scale = C.dw_scale.as<float>(); dw.shift = C.dw_shift.as<float>();
-      dw.out = xbf.p; dw.out_plane = xbf.plane; dw.ldo = A; dw.planes = P;
+      dw.out = xbf.p; dw.out_plane = xbf.plane; dw.ldo = A; dw.planes = P; dw.fp16 = FP;
       p.step(nm + "_dwconv", [dw, B](cudaStream_t st) { return launch_glu_dwconv(dw, B, st); });
       GemmDesc d2 = p.linear(xbf, A, R, C.pw2);
       d2.residual = hx; d2.ldr = A; d2.out_f32 = hx; d2.ldo = A;
@@ -752,9 +786,15 @@ int seg_run(dz_seg* s, const float* wav, int B, int N, float* logp, uint8_t* ml,
   if (!s->finalized) return fail(DZ_ERR_STATE, "dz_seg_finalize has not been called");
   if (B <= 0 || N <= 0) return fail(DZ_ERR_INVALID, "bad batch shape");
   if (s->B != B || s->N != N) {
+    cudaDeviceSynchronize();  // re-planning frees the workspace earlier launches may still be using
     int r = plan_impl(s, B, N);
     if (r != DZ_OK) return r;
+    cudaError_t e = cudaDeviceSynchronize();  // workspace memsets (legacy stream) vs. non-blocking caller streams
+    if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("plan failed: ") + cudaGetErrorString(e));
   }
+  if (!s->done_event) cudaEventCreateWithFlags(&s->done_event, cudaEventDisableTiming);
+  // one workspace per engine: a run on another stream must wait for the previous run to finish
+  if (s->ran && s->last_stream != st) cudaStreamWaitEvent(st, s->done_event, 0);
   s->cur_wav = wav; s->cur_logp = logp; s->cur_ml = ml;
   int n = 0;
   for (size_t i = 0; i < s->steps.size(); ++i) {
@@ -764,6 +804,8 @@ int seg_run(dz_seg* s, const float* wav, int B, int N, float* logp, uint8_t* ml,
     ++n;
   }
   s->last_launches = n;
+  cudaEventRecord(s->done_event, st);
+  s->last_stream = st; s->ran = true;
   return DZ_OK;
 }
 
@@ -773,7 +815,7 @@ extern "C" {
 
 dz_seg* dz_seg_create(const dz_seg_arch* arch, int precision, int gemm_impl, int attn_impl) {
   if (!arch) { fail(DZ_ERR_INVALID, "null arch"); return nullptr; }
-  if (precision != 1 && precision != 3) { fail(DZ_ERR_INVALID, "precision must be 1 (bf16) or 3 (bf16x3)"); return nullptr; }
+  if (precision != 1 && precision != 2 && precision != 3) { fail(DZ_ERR_INVALID, "precision must be 1 (bf16), 2 (fp16) or 3 (bf16x3)"); return nullptr; }
   if (arch->num_layers > DZ_MAX_LAYERS || arch->total_heads > DZ_MAX_HEADS) { fail(DZ_ERR_INVALID, "architecture exceeds compiled limits"); return nullptr; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fail(DZ_ERR_CUDA, "no CUDA device: diarizen_b200 has no CPU fallback"); return nullptr; }
@@ -786,6 +828,8 @@ dz_seg* dz_seg_create(const dz_seg_arch* arch, int precision, int gemm_impl, int
   s->arch = *arch;
   s->precision = precision;
   s->planes = precision == 3 ? 2 : 1;
+  s->npass = precision == 3 ? 3 : 1;
+  s->fp16 = precision == 2 ? 1 : 0;
   s->gemm_impl = gemm_impl;
   s->attn_impl = attn_impl;
   return s;
@@ -856,12 +900,12 @@ int dz_seg_forward_host(dz_seg* s, const float* wav_host, int B, int N, float* l
   return DZ_OK;
 }
 
-__global__ void tap_bf_to_f32_kernel(const __nv_bfloat16* p, long long plane, int planes, long long rows, int C, int ld, float* dst) {
+__global__ void tap_bf_to_f32_kernel(const __nv_bfloat16* p, long long plane, int planes, int fp16, long long rows, int C, int ld, float* dst) {
   const long long n = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C; const int c = (int)(i - r * C);
-    float v = __bfloat162float(p[r * ld + c]);
-    if (planes > 1) v += __bfloat162float(p[plane + r * ld + c]);
+    float v = from16(p[r * ld + c], fp16);
+    if (planes > 1) v += from16(p[plane + r * ld + c], fp16);
     dst[i] = v;
   }
 }
@@ -886,7 +930,7 @@ int64_t dz_seg_tap(dz_seg* s, const char* name, float* dst_dev, int64_t capacity
   int r = seg_run(s, s->cur_wav, s->B, s->N, nullptr, nullptr, 0, t.step);
   if (r != DZ_OK) return r;
   if (t.f32) tap_f32_kernel<<<592, 256>>>(t.f32, t.rows, t.C, t.ld, dst_dev);
-  else tap_bf_to_f32_kernel<<<592, 256>>>(t.bf, t.bf_plane, s->planes, t.rows, t.C, t.ld, dst_dev);
+  else tap_bf_to_f32_kernel<<<592, 256>>>(t.bf, t.bf_plane, s->planes, s->fp16, t.rows, t.C, t.ld, dst_dev);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("tap failed: ") + cudaGetErrorString(e));
   return n;

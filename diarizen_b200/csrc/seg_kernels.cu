@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
           v0 = (c < a.C0) ? gelu_erf(v0) : 0.f;
           v1 = (c + 1 < a.C0) ? gelu_erf(v1) : 0.f;
           bf16 h0, l0, h1, l1;
-          split_bf16(v0, h0, l0);
-          split_bf16(v1, h1, l1);
+          split_bf16(v0, h0, l0, a.fp16);
+          split_bf16(v1, h1, l1, a.fp16);
           *reinterpret_cast<__nv_bfloat162*>(oh + c) = __halves2bfloat162(h0, h1);
           if (a.planes > 1) *reinterpret_cast<__nv_bfloat162*>(oh + a.out_plane + c) = __halves2bfloat162(l0, l1);
         }
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(LnArgs a) {
       if (c + 3 < a.ldb) {  // ldb % 8 == 0: whole chunk inside the (zero padded) row
         bf16 h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(v[4 * i + j], h[j], l[j]);
+        for (int j = 0; j < 4; ++j) split_bf16(v[4 * i + j], h[j], l[j], a.fp16);
         uint2 hw, lw;
         hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
         hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
@@ -384,7 +384,7 @@ cudaError_t launch_axpy_mix(const float* x, float* mix, float w, int init, long 
 // ------------------------------------------------------------------------------------------------
 __global__ void regroup_to_bf16_kernel(const float* __restrict__ x, long long rows, int C, int ldx, int seq_len,
                                        int seq_rows_out, int row_off, int gin, int gout, bf16* __restrict__ out,
-                                       long long out_plane, int ldo, int planes) {
+                                       long long out_plane, int ldo, int planes, int fp16) {
   const long long total = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
@@ -393,18 +393,18 @@ __global__ void regroup_to_bf16_kernel(const float* __restrict__ x, long long ro
     const int t = (int)(r - sb * seq_len);
     const float v = x[r * ldx + c];
     bf16 h, l;
-    split_bf16(v, h, l);
+    split_bf16(v, h, l, fp16);
     const long long o = (sb * seq_rows_out + t + row_off) * ldo + (c / gin) * gout + (c % gin);
     out[o] = h;
     if (planes > 1) out[out_plane + o] = l;
   }
 }
 cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int seq_len, int seq_rows_out, int row_off,
-                           int gin, int gout, bf16* out, long long out_plane, int ldo, int planes, cudaStream_t st) {
+                           int gin, int gout, bf16* out, long long out_plane, int ldo, int planes, int fp16, cudaStream_t st) {
   const long long total = rows * C;
   const int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   regroup_to_bf16_kernel<<<grid, 256, 0, st>>>(x, rows, C, ldx, seq_len, seq_rows_out, row_off, gin, gout, out, out_plane,
-                                               ldo, planes);
+                                               ldo, planes, fp16);
   return cudaGetLastError();
 }
 
@@ -427,10 +427,10 @@ __global__ void __launch_bounds__(256) relpos_gate_kernel(GateArgs a) {
   for (int hi = 0; hi < a.nheads; ++hi) {
     const int h = a.head_index[hi];
     const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(xr + h * 64 + 2 * lane);
-    float x0 = __bfloat162float(xv.x), x1 = __bfloat162float(xv.y);
+    float x0 = from16(xv.x, a.fp16), x1 = from16(xv.y, a.fp16);
     if (a.planes > 1) {
       const __nv_bfloat162 xl = *reinterpret_cast<const __nv_bfloat162*>(xr + a.x_plane + h * 64 + 2 * lane);
-      x0 += __bfloat162float(xl.x); x1 += __bfloat162float(xl.y);
+      x0 += from16(xl.x, a.fp16); x1 += from16(xl.y, a.fp16);
     }
     const float sa = warp_sum(wa0 * x0 + wa1 * x1) + a.ba;
     const float sb2 = warp_sum(wb0 * x0 + wb1 * x1) + a.bb;
@@ -472,8 +472,8 @@ __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
     const bf16* qp = a.q + ((long long)b * T + (qvalid ? tq : 0)) * a.ldqk + a.q_col + hi * 64;
 #pragma unroll
     for (int d = 0; d < 64; ++d) {
-      float v = __bfloat162float(qp[d]);
-      if (two) v += __bfloat162float(qp[a.qk_plane + d]);
+      float v = from16(qp[d], a.fp16);
+      if (two) v += from16(qp[a.qk_plane + d], a.fp16);
       q[d] = v;
       o[d] = 0.f;
     }
@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
       float v = 0.f;
       if (k0 + j < T) {
         const bf16* kp = a.k + ((long long)b * T + k0 + j) * a.ldqk + a.k_col + hi * 64 + d;
-        v = __bfloat162float(*kp);
-        if (two) v += __bfloat162float(kp[a.qk_plane]);
+        v = from16(*kp, a.fp16);
+        if (two) v += from16(kp[a.qk_plane], a.fp16);
       }
       Ks[i] = v;
     }
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
       float v = 0.f;
       if (k0 + j < T) {
         const bf16* vp = a.vt + ((long long)b * a.nheads * 64 + hi * 64 + d) * a.ldvt + k0 + j;
-        v = __bfloat162float(*vp);
-        if (two) v += __bfloat162float(vp[a.vt_plane]);
+        v = from16(*vp, a.fp16);
+        if (two) v += from16(vp[a.vt_plane], a.fp16);
       }
       Vs[i] = v;
     }
@@ -550,8 +550,8 @@ __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
 #pragma unroll
     for (int d = 0; d < 64; d += 2) {
       bf16 h0, l0, h1, l1;
-      split_bf16(o[d] * inv, h0, l0);
-      split_bf16(o[d + 1] * inv, h1, l1);
+      split_bf16(o[d] * inv, h0, l0, a.fp16);
+      split_bf16(o[d + 1] * inv, h1, l1, a.fp16);
       *reinterpret_cast<__nv_bfloat162*>(op + d) = __halves2bfloat162(h0, h1);
       if (a.out_planes > 1) *reinterpret_cast<__nv_bfloat162*>(op + a.out_plane + d) = __halves2bfloat162(l0, l1);
     }
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(DwArgs a) {
       float y = acc * sc + sh;
       y = y / (1.f + expf(-y));
       bf16 h, l;
-      split_bf16(y, h, l);
+      split_bf16(y, h, l, a.fp16);
       const long long o = ((long long)b * a.T + t) * a.ldo + c;
       a.out[o] = h;
       if (a.planes > 1) a.out[a.out_plane + o] = l;

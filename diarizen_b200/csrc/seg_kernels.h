@@ -13,7 +13,7 @@ struct Conv0Args {
   const float* wstats;   // large: [B][2] (mean, rstd) of the waveform
   const float* coef;     // base: [B][C0][2] GroupNorm scale/shift
   const float* gamma; const float* beta;  // large: LayerNorm(C0) affine
-  __nv_bfloat16* out; long long out_plane; long long out_bstride; int ldo; int planes;
+  __nv_bfloat16* out; long long out_plane; long long out_bstride; int ldo; int planes; int fp16;
 };
 
 struct LnArgs {
@@ -22,6 +22,7 @@ struct LnArgs {
   float* y_f32; int ldy;
   __nv_bfloat16* y_bf; long long bf_plane; int ldb; int planes;
   float* mix; float mix_w; int mix_src; /*0 none, 1 input x, 2 output y*/ int mix_init;
+  int fp16;
 };
 
 struct GateArgs {
@@ -32,11 +33,12 @@ struct GateArgs {
   const int* head_index;    // [nheads] device
   int nheads;
   float* gate;        // [B][nheads][T]
+  int fp16;
 };
 
-struct AttnArgs {
+struct AttnArgs {   // layout mirrors dz_attn_args (include/diarizen_b200.h)
   int T; int nheads;
-  const __nv_bfloat16* q; const __nv_bfloat16* k; long long qk_plane; int ldqk; int q_col; int k_col;
+  const __nv_bfloat16* q; const __nv_bfloat16* k; long long qk_plane; int ldqk; int q_col; int k_col; int fp16;
   const __nv_bfloat16* vt; long long vt_plane; int ldvt;   // [B][nheads*64][ldvt]
   int planes;
   const float* bias_tab;   // [nheads][2T-1] or null
@@ -48,7 +50,7 @@ struct DwArgs {
   const float* x; int ldx; int T; int A; int ksize;
   const float* w;      // [A][ksize]
   const float* scale; const float* shift;  // folded BatchNorm (+ conv bias)
-  __nv_bfloat16* out; long long out_plane; int ldo; int planes;
+  __nv_bfloat16* out; long long out_plane; int ldo; int planes; int fp16;
 };
 
 struct HeadArgs {
@@ -66,10 +68,14 @@ cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st);
 cudaError_t launch_axpy_mix(const float* x, float* mix, float w, int init, long long n, cudaStream_t st);
 cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int seq_len, int seq_rows_out, int row_off,
                            int gin, int gout, __nv_bfloat16* out, long long out_plane, int ldo, int planes,
-                           cudaStream_t st);
+                           int fp16, cudaStream_t st);
 cudaError_t launch_gate(const GateArgs& a, cudaStream_t st);
 cudaError_t launch_attention_simt(const AttnArgs& a, int B, cudaStream_t st);
 cudaError_t launch_attention_tc(const AttnArgs& a, int B, cudaStream_t st);
+struct AttnPlan;  // tensor maps + launch geometry of the tcgen05 attention kernel (attention_tc.cu)
+AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B);
+void attention_tc_plan_destroy(AttnPlan* p);
+cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st);
 cudaError_t launch_glu_dwconv(const DwArgs& a, int B, cudaStream_t st);
 cudaError_t launch_classifier_head(const HeadArgs& a, cudaStream_t st);
 

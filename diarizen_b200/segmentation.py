@@ -34,10 +34,11 @@ def _arch_to_c(a: SegArch) -> _lib.SegArchC:
 
 
 class SegmentationModel:
-    """precision: "bf16" (one tensor-core pass, tolerance 1e-2 on log-probs) or "bf16x3" (split
-    precision, fp32-class, tolerance 1e-3)."""
+    """precision: "fp16" (one tensor-core pass over IEEE-half operands, fp32 accumulation; log-probs within 1e-2),
+    "bf16" (one pass over bfloat16 operands; ~4x the rounding error of fp16) or "bf16x3" (split precision,
+    fp32-class, log-probs within 1e-3)."""
 
-    def __init__(self, arch: SegArch, state_dict: Dict[str, torch.Tensor], precision: str = "bf16",
+    def __init__(self, arch: SegArch, state_dict: Dict[str, torch.Tensor], precision: str = "fp16",
                  gemm_impl: str = "tc", attn_impl: str = "tc", device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("diarizen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -45,7 +46,7 @@ class SegmentationModel:
         self.device = torch.device(device if device is not None else "cuda")
         self.precision = precision
         self._L = _lib.lib()
-        prec = {"bf16": 1, "bf16x3": 3}[precision]
+        prec = {"bf16": 1, "fp16": 2, "bf16x3": 3}[precision]
         with torch.cuda.device(self.device):
             self._h = self._L.dz_seg_create(C.byref(_arch_to_c(arch)), prec, {"tc": 0, "simt": 1}[gemm_impl],
                                             {"tc": 0, "simt": 1}[attn_impl])

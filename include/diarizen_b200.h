@@ -43,7 +43,7 @@ typedef struct dz_gemm_desc {
   int32_t M, N, K, npass, batches, groups;
   const void* a; /* bf16 */
   int64_t a_plane, a_bstride, a_gstride, a_rstride;
-  int32_t a_kinner, _pad0;
+  int32_t a_kinner, fp16; /* fp16: 0 = operands are bfloat16 bits, 1 = IEEE half bits */
   int64_t a_kouter, a_rows_alloc;
   const void* b; /* bf16 [groups][N][ldb] */
   int64_t b_plane, b_gstride;
@@ -75,7 +75,19 @@ int dz_gemm(const dz_gemm_desc* d, int impl, int force_bn, void* stream);
  * [C, ldb) zeroed).  mix (optional): mix[rows][ldx] = (mix_init ? 0 : mix) + mix_w * (mix_src==1 ? x : y). */
 int dz_layernorm(const float* x_dev, int64_t rows, int C, int ldx, const float* prescale_dev, const float* gamma_dev,
                  const float* beta_dev, int act, float* y_f32_dev, int ldy, void* y_bf_dev, int64_t bf_plane,
-                 int ldb, int planes, float* mix_dev, float mix_w, int mix_src, int mix_init, void* stream);
+                 int ldb, int planes, float* mix_dev, float mix_w, int mix_src, int mix_init, int fp16, void* stream);
+
+/* Attention over q|k row-major planes and v^T planes (layout: csrc/seg_kernels.h AttnArgs, same field order).
+ *   scores = q.k (+ gate[b][h][q] * bias_tab[h][k - q + T - 1]); softmax over k; out = P v.   q is pre-scaled.
+ * impl: 0 = tcgen05 kernel (hi planes only), 1 = CUDA-core kernel (hi + lo planes, fp32). */
+typedef struct dz_attn_args {
+  int32_t T, nheads;
+  const void* q; const void* k; int64_t qk_plane; int32_t ldqk, q_col, k_col, fp16;
+  const void* vt; int64_t vt_plane; int32_t ldvt, planes;
+  const float* bias_tab; const float* gate;
+  void* out; int64_t out_plane; int32_t ldo, out_planes;
+} dz_attn_args;
+int dz_attention(const dz_attn_args* a, int B, int impl, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Segmentation engine
@@ -95,8 +107,9 @@ typedef struct dz_seg_arch {
 
 typedef struct dz_seg dz_seg;
 
-/* precision: 1 = bf16 tensor-core passes, 3 = bf16x3 split (fp32-class).  gemm_impl: 0 tcgen05, 1 CUDA-core.
- * attn_impl: 0 tcgen05, 1 CUDA-core. */
+/* precision: 1 = bf16 operands, one tensor-core pass; 2 = fp16 operands (11-bit mantissa, saturating), one pass;
+ * 3 = bf16x3 split (hi*hi + lo*hi + hi*lo, fp32-class).  Accumulation, residual stream, LayerNorm, softmax are fp32
+ * in every mode.  gemm_impl: 0 tcgen05, 1 CUDA-core.  attn_impl: 0 tcgen05, 1 CUDA-core. */
 dz_seg* dz_seg_create(const dz_seg_arch* arch, int precision, int gemm_impl, int attn_impl);
 void dz_seg_destroy(dz_seg* s);
 /* Parameters are passed by their reference state_dict name (fp32, host memory, C-contiguous). */
