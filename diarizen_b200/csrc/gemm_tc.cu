@@ -1,11 +1,17 @@
-// tcgen05 GEMM for sm_100a:  C = epilogue(A * B^T), bf16 operands (hi/lo planes), fp32 accumulation in TMEM.
+// tcgen05 GEMM for sm_100a:  C = epilogue(A * B^T), 16-bit operands (hi/lo planes), fp32 accumulation in TMEM.
 //
-// One CTA computes a 128 x BN output tile.  Warp roles:
+// Persistent kernel: one CTA per SM walks the 128 x BN output tiles (n fastest, so that the CTAs running
+// at the same time share A rows through L2).  Warp roles:
 //   warp 0      : TMA producer (one elected lane): A box 128 rows x 64 k, B box BN rows x 64 k, SWIZZLE_128B
 //   warp 1      : TMEM allocator + UMMA issuer (one elected lane): 4 x tcgen05.mma (K = 16) per 64-wide k block
-//   warps 2..5  : epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias/act/residual -> HBM
+//   warps 2..9  : epilogue.  The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i
+//                 overlaps the main loop of tile i+1.  Each epilogue warp owns 32 accumulator rows (its TMEM lane
+//                 quarter) and every other 32-column chunk: tcgen05.ld -> registers -> 32x32 transpose through a
+//                 private shared-memory patch -> row-wise pass in which a warp touches 128 contiguous bytes of one
+//                 output row per instruction (bias / activation / residual / fp32 + 16-bit plane stores), with the
+//                 residual loads of 8 rows in flight per warp.
 // Pipeline: NSTAGE-deep smem ring with full/empty mbarriers; tcgen05.commit releases a stage back to the
-// producer and finally signals the epilogue.  With npass = 3 the k loop runs three times over
+// producer and signals the epilogue.  With npass = 3 the k loop runs three times over
 // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) into the same accumulator.
 //
 // This kernel replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv1d on the reference hot path
@@ -22,15 +28,18 @@ namespace dz {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+static constexpr int PATCH_FLOATS = 32 * 33;
 
 template <int BN>
 struct TcCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int SMEM = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NSTAGE = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int PATCH_BYTES = NUM_EPI_WARPS * PATCH_FLOATS * 4;
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES + PATCH_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct TcMaps {
@@ -38,23 +47,36 @@ struct TcMaps {
   CUtensorMap b[2];
 };
 
+struct TileCoord { int m0, n0, g, b; };
+
+DZ_DEVINL TileCoord decode_tile(const GemmDesc& d, int tile, int mt, int nt, int BN) {
+  // n (or group) fastest, then m, then batch
+  TileCoord c;
+  const int ni = tile % nt;
+  const int r = tile / nt;
+  c.m0 = (r % mt) * BM;
+  c.b = r / mt;
+  if (d.groups > 1) { c.g = ni; c.n0 = 0; }
+  else { c.g = 0; c.n0 = ni * BN; }
+  return c;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int a_rank5) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int a_rank5, const int mt, const int nt,
+               const int ntiles) {
   using C = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
+  float* patches = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES + C::PATCH_BYTES);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
-  uint64_t* tmem_full = empty_bar + C::NSTAGE;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + C::NSTAGE;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int g = (d.groups > 1) ? (int)blockIdx.y : 0;
-  const int n0 = (d.groups > 1) ? 0 : (int)blockIdx.y * BN;
-  const int b = blockIdx.z;
   const int kblocks = (d.K + BK - 1) / BK;
   const int iters = kblocks * d.npass;
 
@@ -63,12 +85,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], NUM_EPI_WARPS); mbar_init(&tmem_empty[1], NUM_EPI_WARPS);
     mbar_fence_init();
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b[0]);
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, BN);
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -76,77 +99,160 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % C::NSTAGE;
-        const uint32_t ph = (it / C::NSTAGE) & 1;
-        const int pass = it / kblocks;
-        const int kb = it - pass * kblocks;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * C::STAGE_BYTES;
-        uint8_t* sb = sa + C::A_BYTES;
-        mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        const CUtensorMap* ma = &maps.a[pass == 1 ? 1 : 0];
-        const CUtensorMap* mb = &maps.b[pass == 2 ? 1 : 0];
-        if (a_rank5) {
-          // (k_inner, k_outer, row, group, batch): one k block = one run of a_kinner (=64) elements
-          tma_load_5d(sa, ma, &full_bar[s], 0, kb, m0, g, b);
-        } else {
-          tma_load_3d(sa, ma, &full_bar[s], kb * BK, m0, b);
+      int gi = 0;  // global k-iteration counter (ring position)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+        for (int it = 0; it < iters; ++it, ++gi) {
+          const int s = gi % C::NSTAGE;
+          const uint32_t ph = (gi / C::NSTAGE) & 1;
+          const int pass = it / kblocks;
+          const int kb = it - pass * kblocks;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          const CUtensorMap* ma = &maps.a[pass == 1 ? 1 : 0];
+          const CUtensorMap* mb = &maps.b[pass == 2 ? 1 : 0];
+          if (a_rank5) {
+            // (k_inner, k_outer, row, group, batch): one k block = one run of a_kinner (=64) elements
+            tma_load_5d(sa, ma, &full_bar[s], 0, kb, tc.m0, tc.g, tc.b);
+          } else {
+            tma_load_3d(sa, ma, &full_bar[s], kb * BK, tc.m0, tc.b);
+          }
+          tma_load_3d(sb, mb, &full_bar[s], kb * BK, tc.n0, tc.g);
         }
-        tma_load_3d(sb, mb, &full_bar[s], kb * BK, n0, g);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const int n_valid = min(BN, d.N - n0);
-      const uint32_t umma_n = (uint32_t)((n_valid + 15) & ~15);
-      const uint32_t idesc = umma_idesc_bf16(BM, umma_n, d.fp16);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % C::NSTAGE;
-        const uint32_t ph = (it / C::NSTAGE) & 1;
-        const int kb = it % kblocks;
-        mbar_wait(&full_bar[s], ph);
+      int gi = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+        const int n_valid = min(BN, d.N - tc.n0);
+        const uint32_t umma_n = (uint32_t)((n_valid + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(BM, umma_n, d.fp16);
+        const int acc = tcount & 1;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t sb = sa + C::A_BYTES;
-        const int krem = d.K - kb * BK;
-        const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adesc = umma_desc_sw128(sa + k * 32);
-          const uint64_t bdesc = umma_desc_sw128(sb + k * 32);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int it = 0; it < iters; ++it, ++gi) {
+          const int s = gi % C::NSTAGE;
+          const uint32_t ph = (gi / C::NSTAGE) & 1;
+          const int kb = it % kblocks;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const int krem = d.K - kb * BK;
+          const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = umma_desc_sw128(sa + k * 32);
+            const uint64_t bdesc = umma_desc_sw128(sb + k * 32);
+            umma_bf16(tmem_acc, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full[acc]);
       }
-      umma_commit(tmem_full);
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int n_valid = min(BN, d.N - n0);
-    const int n_store = max(n_valid, min(BN, d.zero_pad_to - n0));
+    // ---------------- epilogue warps ----------------
+    const int ew = warp - 2;         // 0..7
+    const int quad = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;        // which alternate 32-column chunks this warp takes
+    float* patch = patches + ew * PATCH_FLOATS;
+    const int rm_cols = (d.out_t != nullptr) ? d.tr_col0 : d.N;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+      const int acc = tcount & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16);
+      const int n_valid = min(BN, d.N - tc.n0);
+      const int n_store = max(n_valid, min(BN, d.zero_pad_to - tc.n0));
+      const int mrow0 = tc.m0 + quad * 32;
+      mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      if (c >= n_store) break;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      if (m < d.M) {
-        float v[32];
+      for (int c = half * 32; c < n_store; c += 64) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int ncol0 = tc.n0 + c;
+        // transposed outputs (v^T): thread <-> row, coalesced along rows straight from registers
+        if (d.out_t != nullptr && ncol0 + 32 > d.tr_col0) {
+          const int m = mrow0 + lane;
+          if (m < d.M) {
+            const int sb = m / d.seq_len, st = m - sb * d.seq_len;
+            bf16* tp = (bf16*)d.out_t + (long long)sb * d.ot_bstride + st;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        gemm_epilogue_chunk(d, b, g, m, n0 + c, v);
+            for (int j = 0; j < 32; ++j) {
+              const int n = ncol0 + j;
+              if (n >= d.tr_col0 && n < d.N) {
+                float v = __uint_as_float(r[j]);
+                if (d.bias != nullptr) v += __ldg(d.bias + tc.g * d.group_cols + n);
+                v = d.alpha * apply_act(v, d.act);
+                bf16 h, l;
+                split_bf16(v, h, l, d.fp16);
+                bf16* q = tp + (long long)(n - d.tr_col0) * d.ldt;
+                *q = h;
+                if (d.out_planes > 1) q[d.ot_plane] = l;
+              }
+            }
+          }
+        }
+        // row-major outputs: 32x32 transpose through the warp's private patch, then one output row per instruction
+        if (ncol0 < max(rm_cols, d.zero_pad_to) || d.out_f32 != nullptr || d.residual != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int n = ncol0 + lane;
+          const float bias_v = (d.bias != nullptr && n < d.N) ? __ldg(d.bias + tc.g * d.group_cols + n) : 0.f;
+          const bool plain = (d.residual != nullptr) && (n < d.N);
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            float res[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + r0 + i;
+              res[i] = (plain && m < d.M)
+                           ? d.residual[(long long)tc.b * d.res_bstride + (long long)m * d.ldr + tc.g * d.group_cols + n]
+                           : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + r0 + i;
+              if (m >= d.M) continue;
+              const float a = patch[(r0 + i) * 33 + lane];
+              const int gcol = tc.g * d.group_cols + n;
+              if (n < d.N) {
+                const float v = d.alpha * apply_act(a + bias_v, d.act) + res[i];
+                if (d.out_f32 != nullptr) d.out_f32[(long long)tc.b * d.of_bstride + (long long)m * d.ldo + gcol] = v;
+                if (d.out_bf != nullptr && n < rm_cols) {
+                  bf16 h, l;
+                  split_bf16(v, h, l, d.fp16);
+                  bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
+                  *hp = h;
+                  if (d.out_planes > 1) hp[d.ob_plane] = l;
+                }
+              } else if (d.out_bf != nullptr && n < d.zero_pad_to && d.out_t == nullptr) {
+                bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
+                *hp = __float2bfloat16_rn(0.0f);
+                if (d.out_planes > 1) hp[d.ob_plane] = __float2bfloat16_rn(0.0f);
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
+      // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -204,8 +310,20 @@ struct GemmPlan {
   TcMaps maps;
   int bn = 128;
   int rank5 = 0;
+  int mt = 0, nt = 0, ntiles = 0;
   dim3 grid;
 };
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 template <int BN>
 static cudaError_t launch_bn(const GemmPlan* p, cudaStream_t st) {
@@ -215,7 +333,7 @@ static cudaError_t launch_bn(const GemmPlan* p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<p->grid, NUM_THREADS, TcCfg<BN>::SMEM, st>>>(p->maps, p->d, p->rank5);
+  gemm_tc_kernel<BN><<<p->grid, NUM_THREADS, TcCfg<BN>::SMEM, st>>>(p->maps, p->d, p->rank5, p->mt, p->nt, p->ntiles);
   return cudaGetLastError();
 }
 
@@ -262,9 +380,10 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
     uint32_t bbox[3] = {BK, (uint32_t)p->bn, 1};
     if (!make_tmap_bf16(&p->maps.b[pl], bbase, 3, bdims, bstr, bbox)) { delete p; return nullptr; }
   }
-  const int mt = (d.M + BM - 1) / BM;
-  const int nt = d.groups > 1 ? d.groups : (d.N + p->bn - 1) / p->bn;
-  p->grid = dim3(mt, nt, d.batches);
+  p->mt = (d.M + BM - 1) / BM;
+  p->nt = d.groups > 1 ? d.groups : (d.N + p->bn - 1) / p->bn;
+  p->ntiles = p->mt * p->nt * d.batches;
+  p->grid = dim3(p->ntiles < sm_count() ? p->ntiles : sm_count(), 1, 1);
   return p;
 }
 
