@@ -98,6 +98,12 @@ def lib() -> C.CDLL:
     L.dz_relpos_bucket.argtypes = [C.c_int]
     L.dz_gemm.restype = C.c_int
     L.dz_gemm.argtypes = [C.POINTER(GemmDesc), C.c_int, C.c_int, C.c_void_p]
+    L.dz_gemm_plan_create.restype = C.c_void_p
+    L.dz_gemm_plan_create.argtypes = [C.POINTER(GemmDesc), C.c_int]
+    L.dz_gemm_plan_launch.restype = C.c_int
+    L.dz_gemm_plan_launch.argtypes = [C.c_void_p, C.c_void_p]
+    L.dz_gemm_plan_destroy.restype = None
+    L.dz_gemm_plan_destroy.argtypes = [C.c_void_p]
     L.dz_layernorm.restype = C.c_int
     L.dz_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_float,
@@ -138,7 +144,8 @@ def check(rc: int) -> None:
 
 
 EXPORTS = [
-    "dz_last_error", "dz_abi_version", "dz_gemm", "dz_layernorm", "dz_attention",
+    "dz_last_error", "dz_abi_version", "dz_gemm", "dz_gemm_plan_create", "dz_gemm_plan_launch", "dz_gemm_plan_destroy",
+    "dz_layernorm", "dz_attention",
     "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
     "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
     "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",

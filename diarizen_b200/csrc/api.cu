@@ -41,6 +41,19 @@ int dz_gemm(const dz_gemm_desc* d, int impl, int force_bn, void* stream) {
   return e == cudaSuccess ? DZ_OK : fail(DZ_ERR_CUDA, cudaGetErrorString(e));
 }
 
+dz_gemm_plan* dz_gemm_plan_create(const dz_gemm_desc* d, int force_bn) {
+  if (!d) { fail(DZ_ERR_INVALID, "null descriptor"); return nullptr; }
+  GemmPlan* p = gemm_plan_create(*d, force_bn);
+  if (!p) fail(DZ_ERR_CUDA, gemm_last_error());
+  return reinterpret_cast<dz_gemm_plan*>(p);
+}
+int dz_gemm_plan_launch(const dz_gemm_plan* p, void* stream) {
+  if (!p) return fail(DZ_ERR_INVALID, "null plan");
+  cudaError_t e = gemm_plan_launch(reinterpret_cast<const GemmPlan*>(p), (cudaStream_t)stream);
+  return e == cudaSuccess ? DZ_OK : fail(DZ_ERR_CUDA, cudaGetErrorString(e));
+}
+void dz_gemm_plan_destroy(dz_gemm_plan* p) { gemm_plan_destroy(reinterpret_cast<GemmPlan*>(p)); }
+
 int dz_layernorm(const float* x_dev, int64_t rows, int C, int ldx, const float* prescale_dev, const float* gamma_dev,
                  const float* beta_dev, int act, float* y_f32_dev, int ldy, void* y_bf_dev, int64_t bf_plane, int ldb,
                  int planes, float* mix_dev, float mix_w, int mix_src, int mix_init, int fp16, void* stream) {

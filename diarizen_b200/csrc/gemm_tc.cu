@@ -30,7 +30,7 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-static constexpr int PATCH_FLOATS = 32 * 33;
+static constexpr int PATCH_FLOATS = 32 * 36;
 
 template <int BN>
 struct TcCfg {
@@ -59,6 +59,97 @@ DZ_DEVINL TileCoord decode_tile(const GemmDesc& d, int tile, int mt, int nt, int
   if (d.groups > 1) { c.g = ni; c.n0 = 0; }
   else { c.g = 0; c.n0 = ni * BN; }
   return c;
+}
+
+static constexpr int PATCH_LD = 36;  // floats per patch row: 16-byte aligned rows, conflict-free float4 access
+
+template <int ACT>
+DZ_DEVINL float act_t(float x) {
+  if (ACT == 1) return gelu_erf(x);
+  if (ACT == 2) return __fdividef(x, 1.0f + __expf(-x));
+  if (ACT == 3) return fmaxf(x, 0.0f);
+  return x;
+}
+
+// Full 32-column chunk (all columns valid and row-major): lane = (row-in-group of 4, 4-column slot); one warp
+// instruction covers 4 rows x 128 B.  The residual rows of the whole chunk are fetched up front (8 x 16 B per lane).
+template <int ACT>
+DZ_DEVINL void epi_rows_fast(const GemmDesc& d, const TileCoord& tc, const float* patch, int lane, int mrow0, int nrows,
+                             int ncol0) {
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  const int gcol = tc.g * d.group_cols + ncol0 + c4;
+  float4 res[8];
+  const bool has_res = d.residual != nullptr;
+  if (has_res) {
+    const float* resp = d.residual + (long long)tc.b * d.res_bstride + (long long)mrow0 * d.ldr + gcol;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + rsub;
+      res[i] = (r < nrows) ? *reinterpret_cast<const float4*>(resp + r * d.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(d.bias + gcol));
+  float* outp = d.out_f32 ? d.out_f32 + (long long)tc.b * d.of_bstride + (long long)mrow0 * d.ldo + gcol : nullptr;
+  bf16* bfp = d.out_bf ? (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(mrow0 + d.out_row_off) * d.ldob + gcol
+                       : nullptr;
+  const float alpha = d.alpha;
+  const int fp16 = d.fp16;
+  const bool two = d.out_planes > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    if (r >= nrows) continue;
+    float4 v = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + c4);
+    v.x = alpha * act_t<ACT>(v.x + bias.x);
+    v.y = alpha * act_t<ACT>(v.y + bias.y);
+    v.z = alpha * act_t<ACT>(v.z + bias.z);
+    v.w = alpha * act_t<ACT>(v.w + bias.w);
+    if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+    if (outp != nullptr) *reinterpret_cast<float4*>(outp + r * d.ldo) = v;
+    if (bfp != nullptr) {
+      bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(v.x, h0, l0, fp16); split_bf16(v.y, h1, l1, fp16);
+      split_bf16(v.z, h2, l2, fp16); split_bf16(v.w, h3, l3, fp16);
+      uint2 hw;
+      hw.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      hw.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+      *reinterpret_cast<uint2*>(bfp + r * d.ldob) = hw;
+      if (two) {
+        uint2 lw;
+        lw.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        lw.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+        *reinterpret_cast<uint2*>(bfp + d.ob_plane + r * d.ldob) = lw;
+      }
+    }
+  }
+}
+
+// Edge chunk (crosses N, tr_col0 or the zero-pad boundary): element-wise, lane = column.
+__device__ __noinline__ void epi_rows_edge(const GemmDesc& d, const TileCoord& tc, const float* patch, int lane, int mrow0,
+                                           int nrows, int ncol0, int rm_cols) {
+  const int n = ncol0 + lane;
+  const int gcol = tc.g * d.group_cols + n;
+  const float bias_v = (d.bias != nullptr && n < d.N) ? __ldg(d.bias + gcol) : 0.f;
+  for (int r = 0; r < nrows; ++r) {
+    const int m = mrow0 + r;
+    if (n < d.N) {
+      float v = d.alpha * apply_act(patch[r * PATCH_LD + lane] + bias_v, d.act);
+      if (d.residual != nullptr) v += d.residual[(long long)tc.b * d.res_bstride + (long long)m * d.ldr + gcol];
+      if (d.out_f32 != nullptr) d.out_f32[(long long)tc.b * d.of_bstride + (long long)m * d.ldo + gcol] = v;
+      if (d.out_bf != nullptr && n < rm_cols) {
+        bf16 h, l;
+        split_bf16(v, h, l, d.fp16);
+        bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
+        *hp = h;
+        if (d.out_planes > 1) hp[d.ob_plane] = l;
+      }
+    } else if (d.out_bf != nullptr && n < d.zero_pad_to && d.out_t == nullptr) {
+      bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
+      *hp = __float2bfloat16_rn(0.0f);
+      if (d.out_planes > 1) hp[d.ob_plane] = __float2bfloat16_rn(0.0f);
+    }
+  }
 }
 
 template <int BN>
@@ -200,46 +291,24 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
             }
           }
         }
-        // row-major outputs: 32x32 transpose through the warp's private patch, then one output row per instruction
-        if (ncol0 < max(rm_cols, d.zero_pad_to) || d.out_f32 != nullptr || d.residual != nullptr) {
+        // row-major outputs: 32x32 transpose through the warp's private patch, then 4 rows x 128 B per instruction
+        if (ncol0 < max(rm_cols, d.zero_pad_to) || d.out_f32 != nullptr) {
+          float4* prow = reinterpret_cast<float4*>(patch + lane * PATCH_LD);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j)
+            prow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                  __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          const int n = ncol0 + lane;
-          const float bias_v = (d.bias != nullptr && n < d.N) ? __ldg(d.bias + tc.g * d.group_cols + n) : 0.f;
-          const bool plain = (d.residual != nullptr) && (n < d.N);
-#pragma unroll 1
-          for (int r0 = 0; r0 < 32; r0 += 8) {
-            float res[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = mrow0 + r0 + i;
-              res[i] = (plain && m < d.M)
-                           ? d.residual[(long long)tc.b * d.res_bstride + (long long)m * d.ldr + tc.g * d.group_cols + n]
-                           : 0.f;
+          const int nrows = min(32, d.M - mrow0);
+          if (ncol0 + 32 <= rm_cols) {
+            switch (d.act) {
+              case 1: epi_rows_fast<1>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
+              case 2: epi_rows_fast<2>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
+              case 3: epi_rows_fast<3>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
+              default: epi_rows_fast<0>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = mrow0 + r0 + i;
-              if (m >= d.M) continue;
-              const float a = patch[(r0 + i) * 33 + lane];
-              const int gcol = tc.g * d.group_cols + n;
-              if (n < d.N) {
-                const float v = d.alpha * apply_act(a + bias_v, d.act) + res[i];
-                if (d.out_f32 != nullptr) d.out_f32[(long long)tc.b * d.of_bstride + (long long)m * d.ldo + gcol] = v;
-                if (d.out_bf != nullptr && n < rm_cols) {
-                  bf16 h, l;
-                  split_bf16(v, h, l, d.fp16);
-                  bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
-                  *hp = h;
-                  if (d.out_planes > 1) hp[d.ob_plane] = l;
-                }
-              } else if (d.out_bf != nullptr && n < d.zero_pad_to && d.out_t == nullptr) {
-                bf16* hp = (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(m + d.out_row_off) * d.ldob + gcol;
-                *hp = __float2bfloat16_rn(0.0f);
-                if (d.out_planes > 1) hp[d.ob_plane] = __float2bfloat16_rn(0.0f);
-              }
-            }
+          } else {
+            epi_rows_edge(d, tc, patch, lane, mrow0, nrows, ncol0, rm_cols);
           }
           __syncwarp();
         }

@@ -66,6 +66,11 @@ typedef struct dz_gemm_desc {
 
 /* impl: 0 = tcgen05 tensor-core kernel, 1 = CUDA-core checker kernel.  force_bn: 0 auto, or 64/128/256. */
 int dz_gemm(const dz_gemm_desc* d, int impl, int force_bn, void* stream);
+/* Plan once (tensor maps, launch geometry), launch many times (tcgen05 implementation). */
+typedef struct dz_gemm_plan dz_gemm_plan;
+dz_gemm_plan* dz_gemm_plan_create(const dz_gemm_desc* d, int force_bn);
+int dz_gemm_plan_launch(const dz_gemm_plan* p, void* stream);
+void dz_gemm_plan_destroy(dz_gemm_plan* p);
 
 /* ------------------------------------------------------------------------------------------------
  * Element / row kernels of the segmentation path (unit-test surface; the engine calls the same code).
