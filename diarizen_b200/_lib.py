@@ -37,7 +37,13 @@ class GemmDesc(C.Structure):
         ("out_planes", C.c_int32), ("zero_pad_to", C.c_int32),
         ("out_t", C.c_void_p),
         ("ot_plane", C.c_int64), ("ot_bstride", C.c_int64),
-        ("ldt", C.c_int32), ("tr_col0", C.c_int32), ("seq_len", C.c_int32), ("_pad1", C.c_int32),
+        ("ldt", C.c_int32), ("tr_col0", C.c_int32), ("seq_len", C.c_int32), ("act_after_res", C.c_int32),
+        ("conv_runs", C.c_int32), ("conv_run_len", C.c_int32), ("conv_x0", C.c_int32), ("conv_h0", C.c_int32),
+        ("conv_hs", C.c_int32), ("conv_Ho", C.c_int32), ("conv_H", C.c_int32), ("_pad2", C.c_int32),
+        ("a_hstride", C.c_int64),
+        ("res16", C.c_void_p),
+        ("res16_plane", C.c_int64), ("res16_bstride", C.c_int64),
+        ("ldr16", C.c_int32), ("res16_row_off", C.c_int32),
     ]
 
     @classmethod
@@ -134,6 +140,26 @@ def lib() -> C.CDLL:
     L.dz_seg_step_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.dz_seg_profile.restype = C.c_int
     L.dz_seg_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.dz_emb_create.restype = C.c_void_p
+    L.dz_emb_create.argtypes = [C.c_int, C.c_int]
+    L.dz_emb_destroy.restype = None
+    L.dz_emb_destroy.argtypes = [C.c_void_p]
+    L.dz_emb_set_param.restype = C.c_int
+    L.dz_emb_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.dz_emb_finalize.restype = C.c_int
+    L.dz_emb_finalize.argtypes = [C.c_void_p]
+    L.dz_emb_num_fbank_frames.restype = C.c_int
+    L.dz_emb_num_fbank_frames.argtypes = [C.c_int]
+    L.dz_emb_forward.restype = C.c_int
+    L.dz_emb_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.dz_emb_last_launches.restype = C.c_int
+    L.dz_emb_last_launches.argtypes = [C.c_void_p]
+    L.dz_emb_tap_fbank.restype = C.c_int64
+    L.dz_emb_tap_fbank.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.dz_emb_num_steps.restype = C.c_int
+    L.dz_emb_num_steps.argtypes = [C.c_void_p]
+    L.dz_emb_profile.restype = C.c_int
+    L.dz_emb_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -149,4 +175,6 @@ EXPORTS = [
     "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
     "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
     "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",
+    "dz_emb_create", "dz_emb_destroy", "dz_emb_set_param", "dz_emb_finalize", "dz_emb_num_fbank_frames", "dz_emb_forward",
+    "dz_emb_last_launches", "dz_emb_tap_fbank", "dz_emb_num_steps", "dz_emb_profile",
 ]

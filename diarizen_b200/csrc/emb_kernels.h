@@ -1,0 +1,36 @@
+// Argument blocks + launch wrappers of the embedding-path kernels (emb_kernels.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dz {
+
+struct FbankArgs {
+  const float* wav; int N; int F;
+  const float2* twiddle;    // [256] exp(-2 pi i k / 512)
+  const float* window;      // [400] hamming
+  const float* mel_w;       // [80][257]
+  const int* mel_range;     // [80][2] first / one-past-last non-zero FFT bin
+  float* out;               // [B][F][80] log-mel (before mean subtraction)
+};
+struct Conv1Args {
+  const float* fb; const float* mean; int B; int F;
+  const float* w;           // [32][9]
+  const float* scale; const float* shift;   // folded BatchNorm
+  __nv_bfloat16* out; long long out_plane; int planes; int fp16;   // [B][80][F+2][32]
+};
+struct PoolArgs {
+  const __nv_bfloat16* x; long long x_plane; int planes; int fp16;
+  int H; int W; int C;
+  const float* masks; int S; int T;
+  const int* widx;          // [W] nearest-interpolation source frame
+  __nv_bfloat16* out; long long out_plane; int ldo;
+};
+
+cudaError_t launch_fbank(const FbankArgs& a, int B, cudaStream_t st);
+cudaError_t launch_fbank_mean(const float* fb, int B, int F, float* mean, cudaStream_t st);
+cudaError_t launch_emb_conv1(const Conv1Args& a, cudaStream_t st);
+cudaError_t launch_stats_pool(const PoolArgs& a, int B, cudaStream_t st);
+
+}  // namespace dz

@@ -25,9 +25,23 @@ DZ_DEVINL void gemm_epilogue_chunk(const GemmDesc& d, int b, int g, int m, int n
         if (j < nvalid) v[j] += __ldg(d.bias + gcol0 + j);
     }
   }
+  if (d.act_after_res) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = d.alpha * apply_act(v[j], d.act);
+    for (int j = 0; j < 32; ++j) v[j] = d.alpha * v[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = d.alpha * apply_act(v[j], d.act);
+  }
   // ---- residual ----
+  if (d.res16 != nullptr) {
+    const bf16* rp = (const bf16*)d.res16 + (long long)b * d.res16_bstride + (long long)(m + d.res16_row_off) * d.ldr16 + gcol0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) {
+        v[j] += from16(rp[j], d.fp16);
+        if (d.out_planes > 1) v[j] += from16(rp[d.res16_plane + j], d.fp16);
+      }
+  }
   if (d.residual != nullptr) {
     const float* rp = d.residual + (long long)b * d.res_bstride + (long long)m * d.ldr + gcol0;
     if (nvalid >= 32) {
@@ -41,6 +55,10 @@ DZ_DEVINL void gemm_epilogue_chunk(const GemmDesc& d, int b, int g, int m, int n
       for (int j = 0; j < 32; ++j)
         if (j < nvalid) v[j] += rp[j];
     }
+  }
+  if (d.act_after_res) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], d.act);
   }
   // ---- fp32 row-major output ----
   if (d.out_f32 != nullptr) {

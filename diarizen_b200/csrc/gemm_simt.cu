@@ -30,13 +30,26 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
   const __nv_bfloat16* abase = (const __nv_bfloat16*)d.a + (long long)b * d.a_bstride + (long long)g * d.a_gstride;
   const __nv_bfloat16* bbase = (const __nv_bfloat16*)d.b + (long long)g * d.b_gstride;
 
-  for (int k0 = 0; k0 < d.K; k0 += SM_KT) {
+  const bool conv2d = d.conv_runs > 0;
+  const int krun = conv2d ? ((d.conv_run_len + 63) / 64) * 64 : 0;   // padded run length in the B layout
+  const int Ktot = conv2d ? d.conv_runs * krun : d.K;
+  const int img = conv2d ? b / d.conv_Ho : 0, ho = conv2d ? b - img * d.conv_Ho : 0;
+  for (int k0 = 0; k0 < Ktot; k0 += SM_KT) {
     // A tile: 64 rows x 16 k -> 1024 elements, 4 per thread
     for (int e = tid; e < SM_ROWS * SM_KT; e += 256) {
       const int kk = e % SM_KT, rr = e / SM_KT;
       const int k = k0 + kk, m = m0 + rr;
       float v = 0.f;
-      if (k < d.K && m < d.M) {
+      if (conv2d) {
+        const int run = k / krun, kk = k - run * krun;
+        const int hin = d.conv_hs * ho + d.conv_h0 + run;
+        if (k < Ktot && m < d.M && kk < d.conv_run_len && hin >= 0 && hin < d.conv_H) {
+          const __nv_bfloat16* ab = (const __nv_bfloat16*)d.a + (long long)img * d.a_bstride + (long long)hin * d.a_hstride +
+                                    (long long)m * d.a_rstride + d.conv_x0 + kk;
+          v = from16(*ab, d.fp16);
+          if (two) v += from16(ab[d.a_plane], d.fp16);
+        }
+      } else if (k < d.K && m < d.M) {
         const long long off = (long long)m * d.a_rstride + (long long)(k / d.a_kinner) * d.a_kouter + (k % d.a_kinner);
         v = from16(abase[off], d.fp16);
         if (two) v += from16(abase[d.a_plane + off], d.fp16);
@@ -47,7 +60,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
       const int kk = e % SM_KT, nn = e / SM_KT;
       const int k = k0 + kk, n = n0 + nn;
       float v = 0.f;
-      if (k < d.K && n < d.N) {
+      if (k < Ktot && n < d.N) {
         const long long off = (long long)n * d.ldb + k;
         v = from16(bbase[off], d.fp16);
         if (two) v += from16(bbase[d.b_plane + off], d.fp16);

@@ -79,13 +79,36 @@ DZ_DEVINL void epi_rows_fast(const GemmDesc& d, const TileCoord& tc, const float
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   const int gcol = tc.g * d.group_cols + ncol0 + c4;
   float4 res[8];
-  const bool has_res = d.residual != nullptr;
-  if (has_res) {
+  const bool has_res = d.residual != nullptr || d.res16 != nullptr;
+  const int fp16 = d.fp16;
+  if (d.residual != nullptr) {
     const float* resp = d.residual + (long long)tc.b * d.res_bstride + (long long)mrow0 * d.ldr + gcol;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = 4 * i + rsub;
       res[i] = (r < nrows) ? *reinterpret_cast<const float4*>(resp + r * d.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (d.res16 != nullptr) {
+    const bf16* rp = (const bf16*)d.res16 + (long long)tc.b * d.res16_bstride + (long long)(mrow0 + d.res16_row_off) * d.ldr16 + gcol;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + rsub;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows) {
+        const uint2 hw = *reinterpret_cast<const uint2*>(rp + r * d.ldr16);
+        q.x = from16(__ushort_as_bfloat16((unsigned short)(hw.x & 0xffff)), fp16);
+        q.y = from16(__ushort_as_bfloat16((unsigned short)(hw.x >> 16)), fp16);
+        q.z = from16(__ushort_as_bfloat16((unsigned short)(hw.y & 0xffff)), fp16);
+        q.w = from16(__ushort_as_bfloat16((unsigned short)(hw.y >> 16)), fp16);
+        if (d.out_planes > 1) {
+          const uint2 lw = *reinterpret_cast<const uint2*>(rp + d.res16_plane + r * d.ldr16);
+          q.x += from16(__ushort_as_bfloat16((unsigned short)(lw.x & 0xffff)), fp16);
+          q.y += from16(__ushort_as_bfloat16((unsigned short)(lw.x >> 16)), fp16);
+          q.z += from16(__ushort_as_bfloat16((unsigned short)(lw.y & 0xffff)), fp16);
+          q.w += from16(__ushort_as_bfloat16((unsigned short)(lw.y >> 16)), fp16);
+        }
+      }
+      res[i] = q;
     }
   }
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -94,18 +117,24 @@ DZ_DEVINL void epi_rows_fast(const GemmDesc& d, const TileCoord& tc, const float
   bf16* bfp = d.out_bf ? (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(mrow0 + d.out_row_off) * d.ldob + gcol
                        : nullptr;
   const float alpha = d.alpha;
-  const int fp16 = d.fp16;
   const bool two = d.out_planes > 1;
+  const bool after = d.act_after_res != 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + rsub;
     if (r >= nrows) continue;
     float4 v = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + c4);
-    v.x = alpha * act_t<ACT>(v.x + bias.x);
-    v.y = alpha * act_t<ACT>(v.y + bias.y);
-    v.z = alpha * act_t<ACT>(v.z + bias.z);
-    v.w = alpha * act_t<ACT>(v.w + bias.w);
-    if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+    if (after) {
+      v.x = alpha * (v.x + bias.x); v.y = alpha * (v.y + bias.y); v.z = alpha * (v.z + bias.z); v.w = alpha * (v.w + bias.w);
+      if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+      v.x = act_t<ACT>(v.x); v.y = act_t<ACT>(v.y); v.z = act_t<ACT>(v.z); v.w = act_t<ACT>(v.w);
+    } else {
+      v.x = alpha * act_t<ACT>(v.x + bias.x);
+      v.y = alpha * act_t<ACT>(v.y + bias.y);
+      v.z = alpha * act_t<ACT>(v.z + bias.z);
+      v.w = alpha * act_t<ACT>(v.w + bias.w);
+      if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+    }
     if (outp != nullptr) *reinterpret_cast<float4*>(outp + r * d.ldo) = v;
     if (bfp != nullptr) {
       bf16 h0, h1, h2, h3, l0, l1, l2, l3;
@@ -134,8 +163,15 @@ __device__ __noinline__ void epi_rows_edge(const GemmDesc& d, const TileCoord& t
   for (int r = 0; r < nrows; ++r) {
     const int m = mrow0 + r;
     if (n < d.N) {
-      float v = d.alpha * apply_act(patch[r * PATCH_LD + lane] + bias_v, d.act);
-      if (d.residual != nullptr) v += d.residual[(long long)tc.b * d.res_bstride + (long long)m * d.ldr + gcol];
+      float resv = 0.f;
+      if (d.residual != nullptr) resv = d.residual[(long long)tc.b * d.res_bstride + (long long)m * d.ldr + gcol];
+      else if (d.res16 != nullptr) {
+        const bf16* rp = (const bf16*)d.res16 + (long long)tc.b * d.res16_bstride + (long long)(m + d.res16_row_off) * d.ldr16 + gcol;
+        resv = from16(*rp, d.fp16);
+        if (d.out_planes > 1) resv += from16(rp[d.res16_plane], d.fp16);
+      }
+      const float pre = patch[r * PATCH_LD + lane] + bias_v;
+      const float v = d.act_after_res ? apply_act(d.alpha * pre + resv, d.act) : d.alpha * apply_act(pre, d.act) + resv;
       if (d.out_f32 != nullptr) d.out_f32[(long long)tc.b * d.of_bstride + (long long)m * d.ldo + gcol] = v;
       if (d.out_bf != nullptr && n < rm_cols) {
         bf16 h, l;
@@ -168,7 +204,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kblocks = (d.K + BK - 1) / BK;
+  const bool conv2d = d.conv_runs > 0;
+  const int kbpr = conv2d ? (d.conv_run_len + BK - 1) / BK : 0;   // k blocks per input row (conv2d)
+  const int kblocks = conv2d ? d.conv_runs * kbpr : (d.K + BK - 1) / BK;
   const int iters = kblocks * d.npass;
 
   if (threadIdx.x == 0) {
@@ -204,7 +242,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const CUtensorMap* ma = &maps.a[pass == 1 ? 1 : 0];
           const CUtensorMap* mb = &maps.b[pass == 2 ? 1 : 0];
-          if (a_rank5) {
+          if (conv2d) {
+            // (x in padded row, wo, h, image): tap row `run` of output row ho reads input row hs*ho + h0 + run
+            const int run = kb / kbpr, kbr = kb - run * kbpr;
+            const int img = tc.b / d.conv_Ho, ho = tc.b - img * d.conv_Ho;
+            tma_load_4d(sa, ma, &full_bar[s], d.conv_x0 + kbr * BK, tc.m0, d.conv_hs * ho + d.conv_h0 + run, img);
+          } else if (a_rank5) {
             // (k_inner, k_outer, row, group, batch): one k block = one run of a_kinner (=64) elements
             tma_load_5d(sa, ma, &full_bar[s], 0, kb, tc.m0, tc.g, tc.b);
           } else {
@@ -234,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
-          const int krem = d.K - kb * BK;
+          const int krem = conv2d ? d.conv_run_len - (kb % kbpr) * BK : d.K - kb * BK;
           const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = umma_desc_sw128(sa + k * 32);
@@ -422,14 +465,20 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
   p->bn = force_bn ? force_bn : choose_bn(d);
   if (d.groups > 1 && d.N > p->bn) { g_err = "grouped GEMM needs N <= BN"; delete p; return nullptr; }
   if (d.npass != 1 && d.npass != 3) { g_err = "npass must be 1 or 3"; delete p; return nullptr; }
-  p->rank5 = (d.a_kinner != d.K) ? 1 : 0;
+  p->rank5 = (d.conv_runs == 0 && d.a_kinner != d.K) ? 1 : 0;
   const long long rows_alloc = d.a_rows_alloc > 0 ? d.a_rows_alloc : d.M;
   for (int pl = 0; pl < 2; ++pl) {
     const __nv_bfloat16* abase = (const __nv_bfloat16*)d.a + (pl ? d.a_plane : 0);
     const __nv_bfloat16* bbase = (const __nv_bfloat16*)d.b + (pl ? d.b_plane : 0);
     if (pl == 1 && d.npass == 1) { abase = (const __nv_bfloat16*)d.a; bbase = (const __nv_bfloat16*)d.b; }
     bool ok;
-    if (p->rank5) {
+    if (d.conv_runs > 0) {
+      const long long row_elems = d.a_hstride;   // padded input row pitch (Wp * C)
+      uint64_t dims[4] = {(uint64_t)row_elems, (uint64_t)d.M, (uint64_t)d.conv_H, (uint64_t)(d.batches / d.conv_Ho)};
+      uint64_t str[4] = {1, (uint64_t)d.a_rstride, (uint64_t)d.a_hstride, (uint64_t)d.a_bstride};
+      uint32_t box[4] = {BK, BM, 1, 1};
+      ok = make_tmap_bf16(&p->maps.a[pl], abase, 4, dims, str, box);
+    } else if (p->rank5) {
       if (d.a_kinner != BK) { g_err = "rank-5 A operand needs a_kinner == 64"; delete p; return nullptr; }
       uint64_t dims[5] = {(uint64_t)d.a_kinner, (uint64_t)(d.K / d.a_kinner), (uint64_t)rows_alloc,
                           (uint64_t)d.groups, (uint64_t)d.batches};
@@ -444,7 +493,8 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
       ok = make_tmap_bf16(&p->maps.a[pl], abase, 3, dims, str, box);
     }
     if (!ok) { delete p; return nullptr; }
-    uint64_t bdims[3] = {(uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.groups};
+    const int kb_total = d.conv_runs > 0 ? d.conv_runs * ((d.conv_run_len + BK - 1) / BK) * BK : d.K;
+    uint64_t bdims[3] = {(uint64_t)kb_total, (uint64_t)d.N, (uint64_t)d.groups};
     uint64_t bstr[3] = {1, (uint64_t)d.ldb, (uint64_t)(d.groups > 1 ? d.b_gstride : (long long)d.ldb * d.N)};
     uint32_t bbox[3] = {BK, (uint32_t)p->bn, 1};
     if (!make_tmap_bf16(&p->maps.b[pl], bbase, 3, bdims, bstr, bbox)) { delete p; return nullptr; }

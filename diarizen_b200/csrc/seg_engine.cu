@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "seg_kernels.h"
+#include "engine_common.h"
 
 namespace dz {
 
@@ -28,38 +29,9 @@ int fail(int code, const std::string& msg);
 
 static const int CONV_K[7] = {10, 3, 3, 3, 3, 2, 2};
 static const int CONV_S[7] = {5, 2, 2, 2, 2, 2, 2};
-static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
 int relpos_bucket(int d);  // below
 
-struct DevMem {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t alloc(size_t n, bool zero) {
-    release();
-    cudaError_t e = cudaMalloc(&p, n ? n : 16);
-    if (e != cudaSuccess) { p = nullptr; return e; }
-    bytes = n;
-    return zero ? cudaMemset(p, 0, n ? n : 16) : cudaSuccess;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-  ~DevMem() { release(); }
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct Weight {  // GEMM B operand, bf16 planes [2][groups][N][ldb]
-  DevMem w, bias;
-  int N = 0, K = 0, ldb = 0, groups = 1;
-  long long plane = 0, gstride = 0;
-};
-
-struct Planes {  // activation planes view
-  bf16* p = nullptr;
-  long long plane = 0;
-};
-
-typedef std::function<cudaError_t(cudaStream_t)> StepFn;
-struct Step { std::string name; StepFn fn; double flops = 0.0; double bytes = 0.0; };
 struct Tap { int step; const float* f32; const bf16* bf; long long bf_plane; long long rows; int C; int ld; };
 
 }  // namespace dz
@@ -155,70 +127,6 @@ int relpos_bucket(int d) {
   return out + large;
 }
 
-static cudaError_t upload(DevMem& m, const float* h, size_t n) {
-  cudaError_t e = m.alloc(n * sizeof(float), false);
-  if (e != cudaSuccess) return e;
-  return cudaMemcpy(m.p, h, n * sizeof(float), cudaMemcpyHostToDevice);
-}
-static cudaError_t upload_vec(DevMem& m, const std::vector<float>& v) { return upload(m, v.data(), v.size()); }
-
-static inline uint16_t f2bf(float x) {  // round-to-nearest-even, matches __float2bfloat16_rn for finite x
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(r >> 16);
-}
-static inline float bf2f(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float x;
-  memcpy(&x, &u, 4);
-  return x;
-}
-
-static inline uint16_t f2h(float x) {  // fp32 -> IEEE half, round-to-nearest-even, saturating
-  if (x > 65504.f) x = 65504.f;
-  if (x < -65504.f) x = -65504.f;
-  __half h = __float2half_rn(x);  // host-callable conversion (cuda_fp16.h)
-  uint16_t u;
-  memcpy(&u, &h, 2);
-  return u;
-}
-static inline float h2f(uint16_t u) {
-  __half h;
-  memcpy(&h, &u, 2);
-  return __half2float(h);
-}
-static int g_weight_fp16 = 0;  // set by finalize_impl for the duration of the weight build
-
-// w: [groups][N][K] fp32 row-major -> device planes [2][groups][N][ldb]; bias (may be null) -> fp32 padded.
-static cudaError_t make_weight(Weight& W, const float* w, int groups, int N, int K, const float* bias, int nbias) {
-  W.N = N; W.K = K; W.groups = groups;
-  W.ldb = rup(K, 8);
-  W.gstride = (long long)N * W.ldb;
-  W.plane = W.gstride * groups;
-  std::vector<uint16_t> h((size_t)W.plane * 2, 0);
-  for (int g = 0; g < groups; ++g)
-    for (int n = 0; n < N; ++n)
-      for (int k = 0; k < K; ++k) {
-        const float x = w[((size_t)g * N + n) * K + k];
-        const uint16_t hi = g_weight_fp16 ? f2h(x) : f2bf(x);
-        const uint16_t lo = g_weight_fp16 ? f2h(x - h2f(hi)) : f2bf(x - bf2f(hi));
-        const size_t o = (size_t)g * W.gstride + (size_t)n * W.ldb + k;
-        h[o] = hi;
-        h[(size_t)W.plane + o] = lo;
-      }
-  cudaError_t e = W.w.alloc(h.size() * 2, false);
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpy(W.w.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) return e;
-  if (bias != nullptr) {
-    std::vector<float> bb((size_t)rup(nbias, 32) + 32, 0.f);
-    for (int i = 0; i < nbias; ++i) bb[i] = bias[i];
-    e = upload_vec(W.bias, bb);
-  }
-  return e;
-}
-
 struct Builder {
   dz_seg* s;
   int err = 0;
@@ -239,7 +147,7 @@ struct Builder {
 
 static int finalize_impl(dz_seg* s) {
   const dz_seg_arch& a = s->arch;
-  g_weight_fp16 = s->fp16;
+  g_weight_fp16() = s->fp16;
   Builder b{s};
   const std::string fe = "wavlm_model.feature_extractor.";
   const int D = a.embed_dim, H = a.total_heads;

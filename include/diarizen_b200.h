@@ -61,7 +61,15 @@ typedef struct dz_gemm_desc {
   int32_t out_planes, zero_pad_to;
   void* out_t; /* bf16 */
   int64_t ot_plane, ot_bstride;
-  int32_t ldt, tr_col0, seq_len, _pad1;
+  int32_t ldt, tr_col0, seq_len, act_after_res; /* act_after_res: v = act(alpha*(acc+bias) + residual) */
+  /* conv2d mode (conv_runs > 0): A is a zero-bordered NHWC image [b][h][wp][c]; one GEMM "batch" is one output row
+   * (b, ho); K runs over conv_runs input rows, each contributing conv_run_len contiguous elements (kw * C). */
+  int32_t conv_runs, conv_run_len, conv_x0, conv_h0, conv_hs, conv_Ho, conv_H, _pad2;
+  int64_t a_hstride;
+  /* residual read from 16-bit planes (same format as the operands) instead of fp32 */
+  const void* res16;
+  int64_t res16_plane, res16_bstride;
+  int32_t ldr16, res16_row_off;
 } dz_gemm_desc;
 
 /* impl: 0 = tcgen05 tensor-core kernel, 1 = CUDA-core checker kernel.  force_bn: 0 auto, or 64/128/256. */
@@ -139,6 +147,26 @@ int dz_seg_step_info(const dz_seg* s, int i, char* name_buf, int name_cap, doubl
 /* Runs one forward with a CUDA event pair around every launch; ms_out[i] = device time of step i.
  * Returns the number of steps (diagnostic path: events serialise nothing but add ~us per launch). */
 int dz_seg_profile(dz_seg* s, const float* wav_dev, int B, int N, float* ms_out, int cap, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Speaker-embedding engine (WeSpeaker ResNet34)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dz_emb dz_emb;
+dz_emb* dz_emb_create(int precision, int gemm_impl);
+void dz_emb_destroy(dz_emb* s);
+/* state_dict names as in the pyannote checkpoint ("resnet.conv1.weight", ...).  Optional "fbank.mel_banks" [80][257]
+ * and "fbank.window" [400] override the built-in Kaldi tables. */
+int dz_emb_set_param(dz_emb* s, const char* name, const float* host_data, int64_t numel);
+int dz_emb_finalize(dz_emb* s);
+int dz_emb_num_fbank_frames(int num_samples);
+/* wav_dev [B][N] fp32; masks_dev [B][S][T] fp32 (S <= 4 speaker masks per window, T segmentation frames);
+ * emb_dev [B][S][256] fp32.  The trunk runs once per window and is pooled with each of the S masks. */
+int dz_emb_forward(dz_emb* s, const float* wav_dev, const float* masks_dev, int B, int N, int S, int T, float* emb_dev,
+                   void* stream);
+int dz_emb_last_launches(const dz_emb* s);
+int64_t dz_emb_tap_fbank(dz_emb* s, float* dst_dev, int64_t capacity);
+int dz_emb_num_steps(const dz_emb* s);
+int dz_emb_profile(dz_emb* s, float* ms_out, double* flops_out, char* names, int name_stride, int cap, void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,9 @@ def init_resnet_state_dict(seed: int = 0, prefix: str = "resnet.") -> Dict[str, 
             fan_in = 1
             for d in shp[1:]:
                 fan_in *= d
-            t = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5   # He init keeps activations O(1) through 34 layers
+            t = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5   # He init
+            if name.endswith("conv2.weight"):
+                t = t * 0.35                                             # weak residual branches keep the trunk O(10)
         sd[name] = t.float().contiguous()
     return sd
 

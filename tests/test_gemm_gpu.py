@@ -142,3 +142,54 @@ def test_transposed_output(impl):
     vref = ref[:, 2 * h * 64:].view(B, T, h * 64).permute(0, 2, 1)
     _check("vt", (vt[0].double() + vt[1].double())[..., :T], vref, 3)
     assert (vt[..., T:] == 0).all()
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
+@pytest.mark.parametrize("npass", [1, 3])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ks,stride,res", [(2, 10, 50, 32, 32, 3, 1, True), (1, 20, 199, 32, 64, 3, 2, False),
+                                                         (2, 8, 130, 64, 128, 1, 2, False), (1, 6, 300, 128, 128, 3, 1, True),
+                                                         (1, 5, 77, 256, 256, 3, 1, True)])
+def test_conv2d_as_gemm(impl, npass, B, H, W, Cin, Cout, ks, stride, res):
+    """3x3 / 1x1 conv2d (+ folded BN bias, residual from 16-bit planes, ReLU after the add) over a zero-bordered NHWC
+    image == GEMM whose k loop walks the input rows of the window (resnet.py:139-144)."""
+    torch.manual_seed(W)
+    dev = "cuda"
+    x = torch.randn(B, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, ks, ks, device=dev) / (Cin * ks * ks) ** 0.5
+    bias = torch.randn(Cout + 64, device=dev)
+    pad = 1 if ks == 3 else 0
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    Wp, Wop = W + 2, Wo + 2
+    xin = torch.zeros(B, H, Wp, Cin, device=dev)
+    xin[:, :, 1:W + 1] = x.permute(0, 2, 3, 1)
+    xp = to_planes(xin.reshape(B * H * Wp, Cin))                       # (2, B*H*Wp, Cin)
+    xp = torch.cat([xp, torch.zeros(2, 64, Cin, device=dev, dtype=xp.dtype)], dim=1).contiguous()   # slack for tail boxes
+    run_len = ks * Cin
+    krun = rup(run_len, 64)
+    wr = torch.zeros(Cout, ks, krun, device=dev)
+    wr[:, :, :run_len] = w.permute(0, 2, 3, 1).reshape(Cout, ks, ks * Cin)
+    wp = to_planes(wr.reshape(Cout, ks * krun))
+    resid = torch.randn(B, Ho, Wop, Cout, device=dev)
+    resid[:, :, 0] = 0; resid[:, :, -1] = 0
+    rp = to_planes(resid.reshape(B * Ho * Wop, Cout))
+    out = torch.zeros(2, B * Ho * Wop, Cout, device=dev, dtype=torch.bfloat16)
+    d = _lib.GemmDesc.default()
+    d.M, d.N, d.K, d.npass, d.batches = Wo, Cout, ks * krun, npass, B * Ho
+    d.a, d.a_plane, d.a_rstride, d.a_bstride, d.a_hstride = ptr(xp).value, xp[0].numel(), stride * Cin, H * Wp * Cin, Wp * Cin
+    d.a_kinner = d.K
+    d.conv_runs, d.conv_run_len, d.conv_x0, d.conv_h0, d.conv_hs, d.conv_Ho, d.conv_H = ks, run_len, (0 if ks == 3 else Cin), -pad, stride, Ho, H
+    d.b, d.b_plane, d.ldb, d.b_gstride = ptr(wp).value, wp[0].numel(), ks * krun, wp[0].numel()
+    d.bias, d.act, d.act_after_res = ptr(bias).value, 3, 1
+    if res:
+        d.res16, d.res16_plane, d.res16_bstride, d.ldr16, d.res16_row_off = ptr(rp).value, rp[0].numel(), Wop * Cout, Cout, 1
+    d.out_bf, d.ob_plane, d.ob_bstride, d.ldob, d.out_row_off, d.out_planes = ptr(out).value, out[0].numel(), Wop * Cout, Cout, 1, 2
+    run_gemm(d, impl)
+    xv = planes_value(xp, npass)[:B * H * Wp].view(B, H, Wp, Cin)[:, :, 1:W + 1].permute(0, 3, 1, 2)
+    wv = planes_value(wp, npass).view(Cout, ks, krun)[:, :, :run_len].reshape(Cout, ks, ks, Cin).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xv, wv, bias[:Cout].double(), stride=stride, padding=pad)
+    if res:
+        ref = ref + planes_value(rp, 3).view(B, Ho, Wop, Cout)[:, :, 1:Wo + 1].permute(0, 3, 1, 2)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    got = (out[0].double() + out[1].double()).view(B, Ho, Wop, Cout)
+    _check("conv2d", got[:, :, 1:Wo + 1], ref, npass if npass == 1 else 3)
+    assert (got[:, :, 0] == 0).all() and (got[:, :, -1] == 0).all(), "zero border must stay untouched"
