@@ -112,6 +112,7 @@ static int emb_finalize(dz_emb* s) {
   };
   int cin = 32;
   s->blocks.clear();
+  s->blocks.reserve(16);
   for (int li = 0; li < 4; ++li) {
     const int planes = 32 << li;
     for (int bi = 0; bi < NBLOCKS[li]; ++bi) {
@@ -375,6 +376,10 @@ int dz_emb_forward(dz_emb* s, const float* wav_dev, const float* masks_dev, int 
   if (!s->done_event) cudaEventCreateWithFlags(&s->done_event, cudaEventDisableTiming);
   if (s->ran && s->last_stream != st) cudaStreamWaitEvent(st, s->done_event, 0);
   s->cur_wav = wav_dev; s->cur_masks = masks_dev; s->cur_out = emb_dev;
+  {
+    cudaError_t stale = cudaGetLastError();
+    if (stale != cudaSuccess) return fail(DZ_ERR_CUDA, std::string("stale CUDA error before the embedding forward: ") + cudaGetErrorString(stale));
+  }
   int n = 0;
   for (auto& step : s->steps) {
     cudaError_t e = step.fn(st);

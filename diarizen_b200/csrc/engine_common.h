@@ -19,6 +19,14 @@ static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 struct DevMem {
   void* p = nullptr;
   size_t bytes = 0;
+  DevMem() = default;
+  DevMem(const DevMem&) = delete;
+  DevMem& operator=(const DevMem&) = delete;
+  DevMem(DevMem&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevMem& operator=(DevMem&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
   cudaError_t alloc(size_t n, bool zero) {
     release();
     cudaError_t e = cudaMalloc(&p, n ? n : 16);
