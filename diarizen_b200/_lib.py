@@ -160,6 +160,20 @@ def lib() -> C.CDLL:
     L.dz_emb_num_steps.argtypes = [C.c_void_p]
     L.dz_emb_profile.restype = C.c_int
     L.dz_emb_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    for name, args in {
+        "dz_median_filter": [vp, vp, i32, i32, i32, i32, vp],
+        "dz_speaker_count": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
+        "dz_embedding_masks": [vp, i32, i32, i32, i32, vp, vp, vp],
+        "dz_reconstruct": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        "dz_pdist": [vp, i32, i32, vp, vp],
+        "dz_linkage_centroid": [vp, i32, vp, vp, vp],
+        "dz_assign": [vp, i32, i32, i32, vp, vp],
+    }.items():
+        getattr(L, name).restype = C.c_int
+        getattr(L, name).argtypes = args
+    L.dz_linkage_workspace_bytes.restype = i64
+    L.dz_linkage_workspace_bytes.argtypes = [i32]
     _lib = L
     return L
 
@@ -177,4 +191,6 @@ EXPORTS = [
     "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",
     "dz_emb_create", "dz_emb_destroy", "dz_emb_set_param", "dz_emb_finalize", "dz_emb_num_fbank_frames", "dz_emb_forward",
     "dz_emb_last_launches", "dz_emb_tap_fbank", "dz_emb_num_steps", "dz_emb_profile",
+    "dz_median_filter", "dz_speaker_count", "dz_embedding_masks", "dz_reconstruct", "dz_pdist", "dz_linkage_workspace_bytes",
+    "dz_linkage_centroid", "dz_assign",
 ]

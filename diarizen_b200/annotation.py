@@ -1,0 +1,52 @@
+"""Minimal stand-ins for the `pyannote.core` result types the reference returns (pyannote.core is a third-party
+dependency that is not vendored in the reference tree; semantics restated from SURVEY.md Appendix B).
+
+Only what `DiariZenPipeline.__call__` callers use is provided: `Annotation.itertracks(yield_label=True)`, `.uri`,
+`.labels()`, `.to_rttm()` and `Segment(start, end)` (reference: README.md:37-38, diarizen/pipelines/inference.py:184-191).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterator, List, Optional, Tuple
+
+
+@dataclass(frozen=True, order=True)
+class Segment:
+    start: float
+    end: float
+
+    @property
+    def duration(self) -> float:
+        return self.end - self.start
+
+    @property
+    def middle(self) -> float:
+        return 0.5 * (self.start + self.end)
+
+    def __str__(self) -> str:
+        return f"[{self.start:.3f} --> {self.end:.3f}]"
+
+
+class Annotation:
+    def __init__(self, uri: Optional[str] = None):
+        self.uri = uri
+        self._tracks: List[Tuple[Segment, int, object]] = []   # (segment, track, label) in insertion order
+
+    def __setitem__(self, key, label):
+        segment, track = key
+        self._tracks.append((segment, track, label))
+
+    def __len__(self) -> int:
+        return len(self._tracks)
+
+    def labels(self) -> list:
+        return sorted({l for _, _, l in self._tracks})
+
+    def itertracks(self, yield_label: bool = False) -> Iterator:
+        for seg, trk, lab in sorted(self._tracks, key=lambda x: (x[0].start, x[0].end)):
+            yield (seg, trk, lab) if yield_label else (seg, trk)
+
+    def to_rttm(self) -> str:
+        uri = self.uri if self.uri is not None else "<NA>"
+        return "".join(f"SPEAKER {uri} 1 {s.start:.3f} {s.duration:.3f} <NA> <NA> {lab} <NA> <NA>\n"
+                       for s, _, lab in self.itertracks(yield_label=True))

@@ -1,0 +1,394 @@
+// Warp-shuffle / shared-memory kernels of the post-processing stages (no tensor cores here):
+//   median filter of the binarised segmentations, overlap-add speaker counting, embedding mask selection,
+//   cluster-wise reconstruction + per-frame top-count selection, N x N Euclidean distances and the centroid-linkage
+//   agglomerative clustering merge loop (both in float64, operation for operation as scipy computes them),
+//   constrained (one cluster per local speaker) assignment.
+// reference: diarizen/pipelines/inference.py:131-132, pyannote-audio/pyannote/audio/core/inference.py:543-666,
+//   pipelines/utils/diarization.py:122-157,193-239, pipelines/speaker_diarization.py:271-320,377-425,
+//   pipelines/clustering.py:159-173,404-418 (scipy linkage(method="centroid") on unit-norm embeddings).
+#include <string>
+
+#include "../../include/diarizen_b200.h"
+#include "common.cuh"
+
+namespace dz {
+std::string& tls_error();
+int fail(int code, const std::string& msg);
+
+// ------------------------------------------------------------------------------------------------
+// median filter along frames, window `width` (odd), scipy.ndimage 'reflect' boundary (d c b a | a b c d | d c b a).
+// Data are {0,1}: the median is the majority vote.
+// ------------------------------------------------------------------------------------------------
+__global__ void median_filter_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int C, int T, int S, int width) {
+  const long long total = (long long)C * T * S;
+  const int half = width / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % S);
+    const long long r = i / S;
+    const int t = (int)(r % T);
+    const long long c = r / T;
+    int cnt = 0;
+    for (int k = -half; k <= half; ++k) {
+      int tt = t + k;
+      // reflect (edge sample repeated); windows longer than the signal keep folding
+      while (tt < 0 || tt >= T) tt = tt < 0 ? -tt - 1 : 2 * T - tt - 1;
+      cnt += in[(c * T + tt) * S + s];
+    }
+    out[i] = (cnt * 2 > width) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// speaker count: count[f] = rint(mean over the chunks covering frame f of sum_s seg[c][f - start_c][s]) as uint8.
+// start[] is non-decreasing; one thread per output frame gathers its (<= ~10) chunks.
+// ------------------------------------------------------------------------------------------------
+__global__ void speaker_count_kernel(const uint8_t* __restrict__ seg, const int* __restrict__ start, int C, int T, int S, int F,
+                                     int max_count, uint8_t* __restrict__ count) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  // first chunk that can cover f: start_c + T > f ; binary search on the sorted starts
+  int lo = 0, hi = C;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (start[mid] + T > f) hi = mid; else lo = mid + 1; }
+  float sum = 0.f, n = 0.f;
+  for (int c = lo; c < C && start[c] <= f; ++c) {
+    const uint8_t* p = seg + ((long long)c * T + (f - start[c])) * S;
+    int a = 0;
+    for (int s = 0; s < S; ++s) a += p[s];
+    sum += (float)a;
+    n += 1.f;
+  }
+  float v = (n > 0.f) ? rintf(__fdiv_rn(sum, n)) : 0.f;   // np.rint: half to even
+  int iv = (int)v;
+  if (iv > max_count) iv = max_count;
+  count[f] = (uint8_t)iv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding masks: clean = seg * [sum_s seg < 2]; mask[c][s][:] = clean if sum_t clean > min_frames else seg.
+// also active[c][s] = sum_t seg > 0 and clean_count[c][s] = #frames where s is the ONLY active speaker.
+// One CTA per chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embedding_masks_kernel(const uint8_t* __restrict__ seg, int T, int S, int min_frames,
+                                                              float* __restrict__ masks, int* __restrict__ stats /*[C][S][2]*/) {
+  __shared__ int tot[8], cln[8];
+  const int c = blockIdx.x;
+  if (threadIdx.x < 8) { tot[threadIdx.x] = 0; cln[threadIdx.x] = 0; }
+  __syncthreads();
+  const uint8_t* p = seg + (long long)c * T * S;
+  int lt[4] = {0, 0, 0, 0}, lc[4] = {0, 0, 0, 0};
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int a = 0;
+    for (int s = 0; s < S; ++s) a += p[t * S + s];
+    for (int s = 0; s < S; ++s) { lt[s] += p[t * S + s]; lc[s] += (a < 2) ? p[t * S + s] : 0; }
+  }
+  for (int s = 0; s < S; ++s) { atomicAdd(&tot[s], lt[s]); atomicAdd(&cln[s], lc[s]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * T; i += blockDim.x) {
+    const int s = i / T, t = i - s * T;
+    int a = 0;
+    for (int q = 0; q < S; ++q) a += p[t * S + q];
+    const bool use_clean = cln[s] > min_frames;
+    const uint8_t v = p[t * S + s];
+    masks[((long long)c * S + s) * T + t] = (use_clean && a >= 2) ? 0.f : (float)v;
+  }
+  if (threadIdx.x < S) { stats[(c * S + threadIdx.x) * 2] = tot[threadIdx.x]; stats[(c * S + threadIdx.x) * 2 + 1] = cln[threadIdx.x]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reconstruct + to_diarization: act[f][k] = sum over chunks covering f of max_{s: hard[c][s]==k} seg[c][f-start_c][s];
+// then the count[f] largest activations (stable: lower cluster index wins ties) are switched on.
+// One thread per frame, K <= 32.
+// ------------------------------------------------------------------------------------------------
+__global__ void reconstruct_kernel(const uint8_t* __restrict__ seg, const int8_t* __restrict__ hard, const int* __restrict__ start,
+                                   const uint8_t* __restrict__ count, int C, int T, int S, int K, int F,
+                                   uint8_t* __restrict__ discrete, float* __restrict__ act_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float act[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) act[k] = 0.f;
+  int lo = 0, hi = C;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (start[mid] + T > f) hi = mid; else lo = mid + 1; }
+  for (int c = lo; c < C && start[c] <= f; ++c) {
+    const uint8_t* p = seg + ((long long)c * T + (f - start[c])) * S;
+    unsigned on = 0;   // clusters active in this chunk at this frame (max over local speakers of a 0/1 value)
+    for (int s = 0; s < S; ++s) {
+      const int k = hard[c * S + s];
+      if (k >= 0 && k < 32 && p[s]) on |= 1u << k;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) act[k] += (float)((on >> k) & 1u);
+  }
+  int cnt = count[f];
+  const int Kc = K;   // activations are zero-padded when count exceeds the number of clusters (diarization.py:222-226)
+  unsigned chosen = 0;
+  for (int i = 0; i < cnt && i < 32; ++i) {
+    int best = -1; float bv = -1.f;
+    for (int k = 0; k < 32; ++k) {
+      if (k >= max(Kc, cnt)) break;
+      if ((chosen >> k) & 1u) continue;
+      const float v = (k < Kc) ? act[k] : 0.f;
+      if (v > bv) { bv = v; best = k; }
+    }
+    if (best < 0) break;
+    chosen |= 1u << best;
+  }
+  const int Kout = max(Kc, 1);
+  for (int k = 0; k < Kout; ++k) {
+    discrete[(long long)f * Kout + k] = (chosen >> k) & 1u;
+    if (act_out) act_out[(long long)f * Kout + k] = act[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Euclidean distance matrix in float64, exactly as scipy.spatial.distance.pdist computes it on the float64 copy of the
+// (float32, unit-norm) embeddings: d = sqrt(sum_k (u_k - v_k)^2) accumulated sequentially, no fused multiply-add.
+// 32 x 32 tile of pairs per CTA, rows staged in shared memory.  Writes the full symmetric matrix.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pdist_kernel(const float* __restrict__ X, int N, int D, double* __restrict__ out) {
+  extern __shared__ float sx[];   // [2][32][D + 1]
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int ld = D + 1;
+  float* A = sx;
+  float* B = sx + 32 * ld;
+  for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {
+    const int r = e / D, k = e - r * D;
+    const int gi = bi * 32 + r, gj = bj * 32 + r;
+    A[r * ld + k] = gi < N ? X[(long long)gi * D + k] : 0.f;
+    B[r * ld + k] = gj < N ? X[(long long)gj * D + k] : 0.f;
+  }
+  __syncthreads();
+  const int tj = threadIdx.x & 31, ti0 = threadIdx.x >> 5;   // each thread: column tj, rows ti0, ti0+8, ...
+  for (int q = 0; q < 4; ++q) {
+    const int ti = ti0 + 8 * q;
+    const int gi = bi * 32 + ti, gj = bj * 32 + tj;
+    if (gi >= N || gj >= N) continue;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double dl = __dsub_rn((double)A[ti * ld + k], (double)B[tj * ld + k]);
+      s = __dadd_rn(s, __dmul_rn(dl, dl));
+    }
+    const double dist = (gi == gj) ? 0.0 : __dsqrt_rn(s);
+    out[(long long)gi * N + gj] = dist;
+    out[(long long)gj * N + gi] = dist;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Centroid-linkage agglomerative clustering (scipy.cluster.hierarchy.linkage(method="centroid")), one persistent CTA.
+// Every step merges the globally closest pair of live clusters (x < y slot indices; the merged cluster lives in slot y
+// and gets id N + step) and updates the distances with scipy's Lance-Williams expression in float64, evaluated in the
+// same order and without fused multiply-add:
+//   d(z, x+y) = sqrt((((nx*dxz)*dxz + (ny*dyz)*dyz) - ((nx*ny)*dxy*dxy)/(nx+ny)) / (nx+ny))
+// A nearest-neighbour cache (nn[i], nnd[i] over all live j != i) keeps a step at O(N) plus a few row rescans.
+// Z row = (min id, max id, distance, size).
+// ------------------------------------------------------------------------------------------------
+struct ArgMin { double v; int i; };
+DZ_DEVINL ArgMin amin(ArgMin a, ArgMin b) { return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+DZ_DEVINL ArgMin block_argmin(ArgMin v, ArgMin* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, v.v, o); t.i = __shfl_xor_sync(0xffffffffu, v.i, o);
+    v = amin(v, t);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sc[w] = v;
+  __syncthreads();
+  ArgMin r = (l < nw) ? sc[l] : ArgMin{INFINITY, 0x7fffffff};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, r.v, o); t.i = __shfl_xor_sync(0xffffffffu, r.i, o);
+    r = amin(r, t);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) linkage_centroid_kernel(double* __restrict__ Dm, int N, double* __restrict__ Z,
+                                                                int* __restrict__ size, int* __restrict__ cid, int* __restrict__ nn,
+                                                                double* __restrict__ nnd, int* __restrict__ todo) {
+  __shared__ ArgMin sc[32];
+  __shared__ int s_ntodo;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < N; i += nt) { size[i] = 1; cid[i] = i; }
+  __syncthreads();
+  // initial nearest neighbours: one warp per row
+  for (int i = tid >> 5; i < N; i += nt >> 5) {
+    ArgMin best{INFINITY, 0x7fffffff};
+    const double* row = Dm + (long long)i * N;
+    for (int j = tid & 31; j < N; j += 32)
+      if (j != i) best = amin(best, ArgMin{row[j], j});
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, best.v, o); t.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+      best = amin(best, t);
+    }
+    if ((tid & 31) == 0) { nn[i] = best.i; nnd[i] = best.v; }
+  }
+  __syncthreads();
+  for (int step = 0; step < N - 1; ++step) {
+    // 1. globally closest pair
+    ArgMin best{INFINITY, 0x7fffffff};
+    for (int i = tid; i < N; i += nt)
+      if (size[i] > 0) best = amin(best, ArgMin{nnd[i], i});
+    best = block_argmin(best, sc);
+    int x = best.i, y = nn[x];
+    if (x > y) { const int t = x; x = y; y = t; }
+    const double dxy = Dm[(long long)x * N + y];
+    const int nx = size[x], ny = size[y];
+    __syncthreads();
+    if (tid == 0) {
+      const int ix = cid[x], iy = cid[y];
+      Z[step * 4 + 0] = (double)min(ix, iy);
+      Z[step * 4 + 1] = (double)max(ix, iy);
+      Z[step * 4 + 2] = dxy;
+      Z[step * 4 + 3] = (double)(nx + ny);
+      s_ntodo = 0;
+    }
+    __syncthreads();
+    // 2. Lance-Williams update of row / column y; x dies
+    const double nxy = (double)(nx + ny);
+    const double cxy = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dxy), dxy), nxy);
+    for (int z = tid; z < N; z += nt) {
+      if (size[z] == 0 || z == x || z == y) continue;
+      const double dxz = Dm[(long long)x * N + z], dyz = Dm[(long long)y * N + z];
+      const double t1 = __dmul_rn(__dmul_rn((double)nx, dxz), dxz);
+      const double t2 = __dmul_rn(__dmul_rn((double)ny, dyz), dyz);
+      const double nd = __dsqrt_rn(__ddiv_rn(__dsub_rn(__dadd_rn(t1, t2), cxy), nxy));
+      Dm[(long long)y * N + z] = nd;
+      Dm[(long long)z * N + y] = nd;
+      // nearest-neighbour maintenance for row z
+      const int nz = nn[z];
+      if (nz == x || nz == y) {
+        todo[atomicAdd(&s_ntodo, 1)] = z;          // its cached neighbour changed: rescan
+      } else if (nd < nnd[z]) {
+        nn[z] = y; nnd[z] = nd;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { size[x] = 0; size[y] = nx + ny; cid[y] = N + step; todo[s_ntodo++] = y; }
+    __syncthreads();
+    // 3. rescan the rows whose cached neighbour was invalidated (one warp per row)
+    const int ntodo = s_ntodo;
+    for (int q = tid >> 5; q < ntodo; q += nt >> 5) {
+      const int i = todo[q];
+      ArgMin b2{INFINITY, 0x7fffffff};
+      const double* row = Dm + (long long)i * N;
+      for (int j = tid & 31; j < N; j += 32)
+        if (j != i && size[j] > 0) b2 = amin(b2, ArgMin{row[j], j});
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, b2.v, o); t.i = __shfl_xor_sync(0xffffffffu, b2.i, o);
+        b2 = amin(b2, t);
+      }
+      if ((tid & 31) == 0) { nn[i] = b2.i; nnd[i] = b2.v; }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Constrained assignment (one distinct cluster per local speaker, maximise the summed score): exhaustive search over
+// the S! / (S - min(S,K))! ... injective maps, S <= 4, K <= 32.  One thread per chunk.
+// reference: clustering.py:159-173 (scipy.optimize.linear_sum_assignment(maximize=True) per chunk).
+// ------------------------------------------------------------------------------------------------
+__global__ void assign_kernel(const double* __restrict__ soft, int C, int S, int K, int8_t* __restrict__ hard) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* sc = soft + (long long)c * S * K;
+  const int m = min(S, K);      // pairs to assign
+  int best[4] = {-2, -2, -2, -2};
+  double bestv = -INFINITY;
+  int a[4];
+  // enumerate a[s] in {-1 (unassigned), 0..K-1}, distinct clusters, exactly m assigned
+  const int base = K + 1;
+  int total = 1;
+  for (int s = 0; s < S; ++s) total *= base;
+  for (int code = 0; code < total; ++code) {
+    int t = code, assigned = 0;
+    unsigned used = 0;
+    bool ok = true;
+    double v = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const int k = t % base - 1;
+      t /= base;
+      a[s] = k;
+      if (k >= 0) {
+        if ((used >> k) & 1u) { ok = false; break; }
+        used |= 1u << k;
+        ++assigned;
+        v += sc[s * K + k];
+      }
+    }
+    if (!ok || assigned != m) continue;
+    if (v > bestv) { bestv = v; for (int s = 0; s < S; ++s) best[s] = a[s] >= 0 ? a[s] : -2; }
+  }
+  for (int s = 0; s < S; ++s) hard[c * S + s] = (int8_t)best[s];
+}
+
+}  // namespace dz
+
+using namespace dz;
+#define CK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(DZ_ERR_CUDA, cudaGetErrorString(e__)); } while (0)
+
+extern "C" {
+
+int dz_median_filter(const uint8_t* in_dev, uint8_t* out_dev, int C, int T, int S, int width, void* stream) {
+  if (!in_dev || !out_dev || width < 1 || !(width & 1)) return fail(DZ_ERR_INVALID, "bad argument");
+  const long long total = (long long)C * T * S;
+  median_filter_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in_dev, out_dev, C, T, S, width);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+int dz_speaker_count(const uint8_t* seg_dev, const int32_t* start_dev, int C, int T, int S, int F, int max_count, uint8_t* count_dev, void* stream) {
+  if (!seg_dev || !start_dev || !count_dev) return fail(DZ_ERR_INVALID, "bad argument");
+  speaker_count_kernel<<<(F + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seg_dev, start_dev, C, T, S, F, max_count, count_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+int dz_embedding_masks(const uint8_t* seg_dev, int C, int T, int S, int min_frames, float* masks_dev, int32_t* stats_dev, void* stream) {
+  if (!seg_dev || !masks_dev || !stats_dev || S > 4) return fail(DZ_ERR_INVALID, "bad argument (S <= 4)");
+  embedding_masks_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(seg_dev, T, S, min_frames, masks_dev, stats_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+int dz_reconstruct(const uint8_t* seg_dev, const int8_t* hard_dev, const int32_t* start_dev, const uint8_t* count_dev, int C, int T,
+                   int S, int K, int F, uint8_t* discrete_dev, float* act_dev, void* stream) {
+  if (!seg_dev || !hard_dev || !start_dev || !count_dev || !discrete_dev || K > 32 || K < 1) return fail(DZ_ERR_INVALID, "bad argument (1 <= K <= 32)");
+  reconstruct_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, F, discrete_dev, act_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream) {
+  if (!x_dev || !out_dev || N < 1 || D < 1 || D > 512) return fail(DZ_ERR_INVALID, "bad argument");
+  const size_t smem = sizeof(float) * 2 * 32 * (D + 1);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(pdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+  dim3 grid((N + 31) / 32, (N + 31) / 32);
+  pdist_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x_dev, N, D, out_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+/* workspace_dev: at least dz_linkage_workspace_bytes(N) bytes */
+int64_t dz_linkage_workspace_bytes(int N) { return (int64_t)N * (4 * 4 + 8) + 256; }
+int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream) {
+  if (!dist_dev || !z_dev || !workspace_dev || N < 2) return fail(DZ_ERR_INVALID, "bad argument");
+  char* w = (char*)workspace_dev;
+  double* nnd = (double*)w; w += (size_t)N * 8;
+  int* size = (int*)w; w += (size_t)N * 4;
+  int* cid = (int*)w; w += (size_t)N * 4;
+  int* nn = (int*)w; w += (size_t)N * 4;
+  int* todo = (int*)w;
+  linkage_centroid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist_dev, N, z_dev, size, cid, nn, nnd, todo);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream) {
+  if (!soft_dev || !hard_dev || S < 1 || S > 4 || K < 1 || K > 31) return fail(DZ_ERR_INVALID, "bad argument (S <= 4, K <= 31)");
+  assign_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+
+}  // extern "C"

@@ -168,6 +168,30 @@ int64_t dz_emb_tap_fbank(dz_emb* s, float* dst_dev, int64_t capacity);
 int dz_emb_num_steps(const dz_emb* s);
 int dz_emb_profile(dz_emb* s, float* ms_out, double* flops_out, char* names, int name_stride, int cap, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Post-processing and clustering kernels (all buffers on the device; seg is uint8 {0,1} [C][T][S])
+ * ---------------------------------------------------------------------------------------------- */
+/* scipy.ndimage.median_filter(size=(1,width,1), mode="reflect") on binary data (diarizen/pipelines/inference.py:131-132) */
+int dz_median_filter(const uint8_t* in_dev, uint8_t* out_dev, int C, int T, int S, int width, void* stream);
+/* count[f] = min(rint(mean over covering chunks of #active speakers), max_count); start[c] = first global frame of chunk c
+ * (pipelines/utils/diarization.py:122-157 + core/inference.py:543-666) */
+int dz_speaker_count(const uint8_t* seg_dev, const int32_t* start_dev, int C, int T, int S, int F, int max_count,
+                     uint8_t* count_dev, void* stream);
+/* masks[c][s][t] for the embedding pooling (speaker_diarization.py:271-320); stats[c][s] = (#active frames, #single-speaker frames) */
+int dz_embedding_masks(const uint8_t* seg_dev, int C, int T, int S, int min_frames, float* masks_dev, int32_t* stats_dev,
+                       void* stream);
+/* cluster-wise max, overlap-add sum, per-frame top-count selection (speaker_diarization.py:377-425, diarization.py:193-239);
+ * discrete [F][max(K,1)] uint8, act (optional) [F][max(K,1)] fp32 */
+int dz_reconstruct(const uint8_t* seg_dev, const int8_t* hard_dev, const int32_t* start_dev, const uint8_t* count_dev, int C,
+                   int T, int S, int K, int F, uint8_t* discrete_dev, float* act_dev, void* stream);
+/* full symmetric Euclidean distance matrix [N][N] in float64, bit-compatible with scipy pdist on float64(x) */
+int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream);
+/* scipy linkage(method="centroid") from the distance matrix (destroyed); Z [N-1][4] float64 */
+int64_t dz_linkage_workspace_bytes(int N);
+int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream);
+/* per-chunk constrained assignment maximising the summed soft score (clustering.py:159-173); hard [C][S] int8, -2 = none */
+int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

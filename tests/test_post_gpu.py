@@ -1,0 +1,130 @@
+"""Post-processing / clustering kernels vs the numpy-scipy oracle (oracle/pipeline_oracle.py): bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from diarizen_b200 import _lib
+from oracle import pipeline_oracle as po
+
+pytestmark = pytest.mark.gpu
+vp = C.c_void_p
+
+
+def _seg(Cn, T, S, seed, p_on=0.35):
+    rng = np.random.default_rng(seed)
+    # piecewise-constant activity (so that the median filter and run-length logic see realistic runs) + salt noise
+    seg = np.zeros((Cn, T, S), dtype=np.uint8)
+    for c in range(Cn):
+        for s in range(S):
+            t = 0
+            on = rng.random() < p_on
+            while t < T:
+                run = int(rng.integers(3, 60))
+                seg[c, t:t + run, s] = on
+                t += run
+                on = not on if rng.random() < 0.7 else on
+    noise = rng.random(seg.shape) < 0.03
+    return np.where(noise, 1 - seg, seg).astype(np.uint8)
+
+
+def _starts(Cn, dur, step):
+    fr = po.SlidingWindow(0.0, po.FRAME_DURATION, po.FRAME_STEP)
+    return np.array([fr.closest_frame(c * step + 0.5 * fr.duration) for c in range(Cn)], dtype=np.int32)
+
+
+@pytest.mark.parametrize("Cn,T,S", [(7, 249, 4), (3, 799, 4), (2, 5, 4)])
+def test_median_filter(Cn, T, S):
+    from scipy.ndimage import median_filter
+    seg = _seg(Cn, T, S, 1)
+    d = torch.as_tensor(seg, device="cuda")
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().dz_median_filter(vp(d.data_ptr()), vp(out.data_ptr()), Cn, T, S, 11, None))
+    ref = median_filter(seg.astype(np.float32), size=(1, 11, 1), mode="reflect")
+    assert np.array_equal(out.cpu().numpy().astype(np.float32), ref)
+
+
+@pytest.mark.parametrize("Cn,T,dur", [(51, 249, 5.0), (23, 799, 16.0)])
+def test_count_masks_reconstruct(Cn, T, dur):
+    S = 4
+    step = 0.1 * dur
+    seg = _seg(Cn, T, S, 2)
+    segf = seg.astype(np.float32)
+    start = _starts(Cn, dur, step)
+    count_ref = po.speaker_count(segf, dur, step)
+    F = count_ref.shape[0]
+    L = _lib.lib()
+    dseg = torch.as_tensor(seg, device="cuda")
+    dstart = torch.as_tensor(start, device="cuda")
+    dcount = torch.empty(F, dtype=torch.uint8, device="cuda")
+    _lib.check(L.dz_speaker_count(vp(dseg.data_ptr()), vp(dstart.data_ptr()), Cn, T, S, F, 255, vp(dcount.data_ptr()), None))
+    assert np.array_equal(dcount.cpu().numpy(), count_ref[:, 0])
+    # masks
+    mnf = 2
+    masks_ref = po.embedding_masks(segf, mnf)
+    dm = torch.empty((Cn, S, T), dtype=torch.float32, device="cuda")
+    dst = torch.empty((Cn, S, 2), dtype=torch.int32, device="cuda")
+    _lib.check(L.dz_embedding_masks(vp(dseg.data_ptr()), Cn, T, S, mnf, vp(dm.data_ptr()), vp(dst.data_ptr()), None))
+    assert np.array_equal(dm.cpu().numpy(), masks_ref)
+    st = dst.cpu().numpy()
+    assert np.array_equal(st[..., 0], seg.sum(axis=1))
+    assert np.array_equal(st[..., 1], (seg * (seg.sum(axis=2, keepdims=True) == 1)).sum(axis=1))
+    # reconstruct + top-count
+    rng = np.random.default_rng(3)
+    K = 5
+    hard = np.stack([rng.permutation(K)[:S] for _ in range(Cn)]).astype(np.int8)
+    hard[seg.sum(axis=1) == 0] = -2
+    hard[0, 1] = -2
+    cnt = np.minimum(count_ref, 3).astype(np.int8)
+    disc_ref = po.reconstruct(segf, hard, cnt, dur, step)
+    dh = torch.as_tensor(hard, device="cuda")
+    dc = torch.as_tensor(cnt[:, 0].astype(np.uint8), device="cuda")
+    dd = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+    _lib.check(L.dz_reconstruct(vp(dseg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(dc.data_ptr()), Cn, T, S, K, F,
+                                vp(dd.data_ptr()), None, None))
+    got = dd.cpu().numpy().astype(np.float64)
+    assert got.shape == disc_ref.shape and np.array_equal(got, disc_ref)
+
+
+@pytest.mark.parametrize("n,seed", [(2, 0), (50, 1), (700, 2), (3000, 3)])
+def test_linkage_matches_scipy_bitwise(n, seed):
+    from scipy.cluster.hierarchy import linkage
+    from diarizen_b200.clustering import device_linkage_centroid
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((6, 256))
+    x = (centers[rng.integers(0, 6, n)] + 0.6 * rng.standard_normal((n, 256))).astype(np.float32)
+    x /= np.linalg.norm(x, axis=-1, keepdims=True)
+    Zref = linkage(x, method="centroid", metric="euclidean")
+    Z = device_linkage_centroid(x)
+    assert np.array_equal(Z[:, [0, 1, 3]], Zref[:, [0, 1, 3]]), "merge order differs"
+    assert np.array_equal(Z[:, 2], Zref[:, 2]), f"heights differ by {np.abs(Z[:, 2] - Zref[:, 2]).max():.3e}"
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 7, 12])
+def test_assign_matches_hungarian(K):
+    from scipy.optimize import linear_sum_assignment
+    from diarizen_b200.clustering import device_assign
+    rng = np.random.default_rng(K)
+    soft = 2 - rng.random((200, 4, K)) * 2
+    hard = device_assign(soft)
+    for c in range(soft.shape[0]):
+        ref = -2 * np.ones(4, dtype=np.int8)
+        r, k = linear_sum_assignment(soft[c], maximize=True)
+        ref[r] = k
+        assert np.array_equal(hard[c], ref), (c, hard[c], ref)
+
+
+def test_clustering_call_matches_oracle():
+    from diarizen_b200.clustering import AgglomerativeClustering
+    rng = np.random.default_rng(5)
+    Cn, T, S = 300, 249, 4
+    seg = _seg(Cn, T, S, 6).astype(np.float32)
+    protos = rng.standard_normal((5, 256)).astype(np.float32)
+    emb = (protos[rng.integers(0, 5, (Cn, S))] + 0.35 * rng.standard_normal((Cn, S, 256))).astype(np.float32)
+    cl = AgglomerativeClustering()
+    cl.threshold, cl.min_cluster_size = 0.7, 10
+    hard, soft, cent = cl(emb, seg, min_clusters=1, max_clusters=20)
+    href, sref, cref = po.cluster_call(emb, seg, 0.7, 10, 1, 20)
+    assert np.array_equal(hard, href)
+    assert np.allclose(soft, sref, atol=1e-12) and np.allclose(cent, cref, atol=1e-6)
