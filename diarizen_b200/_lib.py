@@ -165,7 +165,7 @@ def lib() -> C.CDLL:
         "dz_median_filter": [vp, vp, i32, i32, i32, i32, vp],
         "dz_speaker_count": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "dz_embedding_masks": [vp, i32, i32, i32, i32, vp, vp, vp],
-        "dz_reconstruct": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        "dz_reconstruct": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
         "dz_pdist": [vp, i32, i32, vp, vp],
         "dz_linkage_centroid": [vp, i32, vp, vp, vp],
         "dz_assign": [vp, i32, i32, i32, vp, vp],

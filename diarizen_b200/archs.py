@@ -283,3 +283,68 @@ def init_state_dict(a: SegArch, seed: int = 0, classifier_gain: float = 1.0) -> 
                 t = t * classifier_gain
         sd[name] = t.to(torch.float32).contiguous()
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------
+# WeSpeaker ResNet34 embedding network (reference: pyannote-audio/pyannote/audio/models/embedding/wespeaker/resnet.py:213-260)
+# ---------------------------------------------------------------------------------------------------------
+RESNET34_BLOCKS = (3, 4, 6, 3)
+M_CHANNELS = 32
+NUM_MEL = 80
+EMB_DIM = 256
+
+
+def resnet_param_shapes(prefix: str = "resnet.") -> Dict[str, tuple]:
+    """State-dict layout of WeSpeakerResNet34 (keys as in the pyannote checkpoint: `resnet.*`)."""
+    P: Dict[str, tuple] = {}
+
+    def bn(name, c):
+        for leaf in ("weight", "bias", "running_mean", "running_var"):
+            P[f"{name}.{leaf}"] = (c,)
+
+    P[prefix + "conv1.weight"] = (M_CHANNELS, 1, 3, 3)
+    bn(prefix + "bn1", M_CHANNELS)
+    cin = M_CHANNELS
+    for li, nb in enumerate(RESNET34_BLOCKS):
+        planes = M_CHANNELS * (2 ** li)
+        for bi in range(nb):
+            stride = (1 if li == 0 else 2) if bi == 0 else 1
+            b = f"{prefix}layer{li + 1}.{bi}."
+            P[b + "conv1.weight"] = (planes, cin, 3, 3)
+            bn(b + "bn1", planes)
+            P[b + "conv2.weight"] = (planes, planes, 3, 3)
+            bn(b + "bn2", planes)
+            if stride != 1 or cin != planes:
+                P[b + "shortcut.0.weight"] = (planes, cin, 1, 1)
+                bn(b + "shortcut.1", planes)
+            cin = planes
+    P[prefix + "seg_1.weight"] = (EMB_DIM, (NUM_MEL // 8) * M_CHANNELS * 8 * 2)
+    P[prefix + "seg_1.bias"] = (EMB_DIM,)
+    return P
+
+
+def init_resnet_state_dict(seed: int = 0, prefix: str = "resnet.") -> Dict[str, torch.Tensor]:
+    """Seeded random-init weights with the shapes above (no checkpoint is reachable offline)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shp in resnet_param_shapes(prefix).items():
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "running_mean":
+            t = 0.05 * torch.randn(shp, generator=g)
+        elif leaf == "running_var":
+            t = 0.8 + 0.4 * torch.rand(shp, generator=g)
+        elif ("bn" in name or "shortcut.1" in name) and leaf == "weight":
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif leaf == "bias":
+            t = 0.05 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5   # He init
+            if name.endswith("conv2.weight"):
+                t = t * 0.35                                             # weak residual branches keep the trunk O(10)
+        sd[name] = t.float().contiguous()
+    return sd
+
+

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) embedding_masks_kernel(const uint8_t* __r
 // One thread per frame, K <= 32.
 // ------------------------------------------------------------------------------------------------
 __global__ void reconstruct_kernel(const uint8_t* __restrict__ seg, const int8_t* __restrict__ hard, const int* __restrict__ start,
-                                   const uint8_t* __restrict__ count, int C, int T, int S, int K, int F,
+                                   const uint8_t* __restrict__ count, int C, int T, int S, int K, int Kout, int F,
                                    uint8_t* __restrict__ discrete, float* __restrict__ act_out) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
@@ -119,24 +119,21 @@ __global__ void reconstruct_kernel(const uint8_t* __restrict__ seg, const int8_t
 #pragma unroll
     for (int k = 0; k < 32; ++k) act[k] += (float)((on >> k) & 1u);
   }
-  int cnt = count[f];
-  const int Kc = K;   // activations are zero-padded when count exceeds the number of clusters (diarization.py:222-226)
+  const int cnt = min((int)count[f], Kout);
   unsigned chosen = 0;
-  for (int i = 0; i < cnt && i < 32; ++i) {
+  for (int i = 0; i < cnt; ++i) {
     int best = -1; float bv = -1.f;
-    for (int k = 0; k < 32; ++k) {
-      if (k >= max(Kc, cnt)) break;
+    for (int k = 0; k < Kout; ++k) {
       if ((chosen >> k) & 1u) continue;
-      const float v = (k < Kc) ? act[k] : 0.f;
+      const float v = (k < K) ? act[k] : 0.f;   // columns >= K are the zero padding of diarization.py:222-226
       if (v > bv) { bv = v; best = k; }
     }
     if (best < 0) break;
     chosen |= 1u << best;
   }
-  const int Kout = max(Kc, 1);
   for (int k = 0; k < Kout; ++k) {
     discrete[(long long)f * Kout + k] = (chosen >> k) & 1u;
-    if (act_out) act_out[(long long)f * Kout + k] = act[k];
+    if (act_out) act_out[(long long)f * Kout + k] = (k < K) ? act[k] : 0.f;
   }
 }
 
@@ -354,9 +351,10 @@ int dz_embedding_masks(const uint8_t* seg_dev, int C, int T, int S, int min_fram
   return DZ_OK;
 }
 int dz_reconstruct(const uint8_t* seg_dev, const int8_t* hard_dev, const int32_t* start_dev, const uint8_t* count_dev, int C, int T,
-                   int S, int K, int F, uint8_t* discrete_dev, float* act_dev, void* stream) {
-  if (!seg_dev || !hard_dev || !start_dev || !count_dev || !discrete_dev || K > 32 || K < 1) return fail(DZ_ERR_INVALID, "bad argument (1 <= K <= 32)");
-  reconstruct_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, F, discrete_dev, act_dev);
+                   int S, int K, int Kout, int F, uint8_t* discrete_dev, float* act_dev, void* stream) {
+  if (!seg_dev || !hard_dev || !start_dev || !count_dev || !discrete_dev || K > 32 || K < 1 || Kout < K || Kout > 32)
+    return fail(DZ_ERR_INVALID, "bad argument (1 <= K <= Kout <= 32)");
+  reconstruct_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, Kout, F, discrete_dev, act_dev);
   CK_LAUNCH();
   return DZ_OK;
 }

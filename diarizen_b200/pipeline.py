@@ -1,0 +1,301 @@
+"""`DiariZenPipeline`: drop-in for the reference class of the same name (diarizen/pipelines/inference.py:26-192).
+
+Same constructor / `from_pretrained` / `__call__` signatures, same result protocol (`itertracks(yield_label=True)`,
+`.uri`, `.to_rttm()`), same config.toml schema.  What differs is where the work happens: every stage between the
+decoded waveform and the final (frames x speakers) decision matrix runs as sm_100a CUDA inside libdiarizen_b200.so -
+sliding-window segmentation, median filter, speaker counting, embedding masks, ResNet34 embeddings, float64 distance
+matrix + centroid linkage, constrained assignment, cluster-wise reconstruction and top-count selection.  The recording
+stays on the device from the first window to the decision matrix; only the embeddings (C x 4 x 256) and a few
+per-chunk counters visit the host, where the reference's own selection logic is applied to them.
+
+Long recordings shard by window range across the ranks of a torch.distributed (NCCL) job: every rank runs the two
+network forwards on its windows, one all-gather collects the binarised segmentations (uint8) and the embeddings, and
+rank 0 clusters and reconstructs (`DiariZenPipeline.__call__` returns the Annotation on rank 0, None elsewhere).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import math
+import os
+import wave
+from pathlib import Path
+from typing import Any, Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .annotation import Annotation, Segment
+from .archs import SegArch, arch_from_reference_config, get_arch, init_state_dict
+from .clustering import AgglomerativeClustering
+from .embedding import EmbeddingModel
+from .segmentation import SegmentationModel
+
+SR = 16000
+FRAME_DURATION = 400 / SR    # receptive field of the conv stack (model_wavlm_conformer.py:126-176)
+FRAME_STEP = 320 / SR
+vp = C.c_void_p
+
+
+def _closest_frame(t: float) -> int:
+    """pyannote.core SlidingWindow.closest_frame with start=0."""
+    return int(np.rint((t - 0.5 * FRAME_DURATION) / FRAME_STEP))
+
+
+def load_waveform(in_wav) -> torch.Tensor:
+    """-> mono (N,) float32 in [-1, 1], 16 kHz.  Stands in for `torchaudio.load(in_wav)[0][0]` (inference.py:127-128)."""
+    if isinstance(in_wav, dict):
+        w = in_wav["waveform"] if "waveform" in in_wav else None
+        if w is None:
+            return load_waveform(in_wav["audio"])
+        if int(in_wav.get("sample_rate", SR)) != SR:
+            raise ValueError("only 16 kHz input is supported")
+        w = torch.as_tensor(w, dtype=torch.float32)
+        return w[0] if w.dim() == 2 else w
+    if isinstance(in_wav, (str, os.PathLike, io.BytesIO)):
+        with wave.open(in_wav if isinstance(in_wav, io.BytesIO) else str(in_wav), "rb") as f:
+            sr, nch, sw, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
+            raw = f.readframes(n)
+        if sr != SR:
+            raise ValueError(f"only 16 kHz input is supported (got {sr} Hz); resample first")
+        if sw == 2:
+            x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif sw == 4:
+            x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif sw == 1:
+            x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError(f"unsupported sample width {sw}")
+        return torch.from_numpy(x.reshape(-1, nch)[:, 0].copy())   # force channel 0 (inference.py:128)
+    raise TypeError(f"input must be either a str, BytesIO or a ProtocolFile; there was {type(in_wav)}")
+
+
+def _load_toml(path: Path) -> dict:
+    import tomllib
+    with open(path, "rb") as f:
+        return tomllib.load(f)
+
+
+class DiariZenPipeline:
+    def __init__(self, diarizen_hub, embedding_model, config_parse: Optional[Dict[str, Any]] = None,
+                 rttm_out_dir: Optional[str] = None, *, precision: str = "fp16", device=None,
+                 _seg: Optional[SegmentationModel] = None, _emb: Optional[EmbeddingModel] = None, _config: Optional[dict] = None):
+        if _config is None:
+            diarizen_hub = Path(diarizen_hub)
+            config = _load_toml(diarizen_hub / "config.toml")
+        else:
+            config = _config
+        if config_parse is not None:
+            print("Overriding with parsed config.")
+            config["inference"]["args"] = config_parse["inference"]["args"]
+            config["clustering"]["args"] = config_parse["clustering"]["args"]
+        inf, clu = config["inference"]["args"], config["clustering"]["args"]
+        self.config = config
+        self.device = torch.device(device if device is not None else "cuda")
+        self.seg_duration = float(inf["seg_duration"])
+        self.segmentation_step = float(inf["segmentation_step"])
+        self.segmentation_batch_size = int(inf["batch_size"])
+        self.embedding_batch_size = int(inf["batch_size"])
+        self.embedding_exclude_overlap = True
+        self.apply_median_filtering = bool(inf["apply_median_filtering"])
+        self.min_speakers = clu["min_speakers"]
+        self.max_speakers = clu["max_speakers"]
+        if clu["method"] == "AgglomerativeClustering":
+            self.clustering = AgglomerativeClustering(metric="cosine", device=self.device)
+            self.clustering.method = "centroid"
+            self.clustering.min_cluster_size = clu["min_cluster_size"]
+            self.clustering.threshold = clu["ahc_threshold"]
+        elif clu["method"] == "VBxClustering":
+            raise NotImplementedError("VBxClustering (PLDA + VB-GMM refinement) is not implemented yet in diarizen_b200; "
+                                      "use clustering.method = 'AgglomerativeClustering' (the recipes' setting)")
+        else:
+            raise ValueError(f"Unsupported clustering method: {clu['method']}")
+        if _seg is None:
+            margs = config["model"]["args"]
+            src = margs.get("wavlm_src", "wavlm_base")
+            sd = torch.load(str(diarizen_hub / "pytorch_model.bin"), map_location="cpu")
+            if os.path.isfile(src):
+                ck = torch.load(src, map_location="cpu")
+                arch = arch_from_reference_config(ck["config"], name=Path(src).stem)
+            else:
+                arch = get_arch(src)
+            _seg = SegmentationModel(arch, sd, precision=precision, device=self.device)
+        if _emb is None:
+            esd = torch.load(str(embedding_model), map_location="cpu")
+            esd = esd.get("state_dict", esd)
+            _emb = EmbeddingModel(esd, precision=precision, device=self.device)
+        self._segmentation = _seg
+        self._embedding = _emb
+        if rttm_out_dir is not None:
+            os.makedirs(rttm_out_dir, exist_ok=True)
+        self.rttm_out_dir = rttm_out_dir
+        self._L = _lib.lib()
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, repo_id: str, cache_dir: str = None, rttm_out_dir: str = None, **kw) -> "DiariZenPipeline":
+        """`repo_id` may be a local directory laid out like the hub snapshot (config.toml, pytorch_model.bin and
+        `wespeaker/pytorch_model.bin` or `embedding.bin`); otherwise the HF hub is queried as the reference does
+        (inference.py:95-119)."""
+        p = Path(repo_id)
+        if p.is_dir():
+            for cand in (p / "wespeaker" / "pytorch_model.bin", p / "embedding.bin"):
+                if cand.exists():
+                    return cls(diarizen_hub=p.expanduser().absolute(), embedding_model=str(cand), rttm_out_dir=rttm_out_dir, **kw)
+            raise FileNotFoundError(f"no embedding checkpoint under {p} (expected wespeaker/pytorch_model.bin)")
+        from huggingface_hub import hf_hub_download, snapshot_download
+        hub = snapshot_download(repo_id=repo_id, cache_dir=cache_dir, local_files_only=cache_dir is not None)
+        emb = hf_hub_download(repo_id="pyannote/wespeaker-voxceleb-resnet34-LM", filename="pytorch_model.bin",
+                              cache_dir=cache_dir, local_files_only=cache_dir is not None)
+        return cls(diarizen_hub=Path(hub).expanduser().absolute(), embedding_model=emb, rttm_out_dir=rttm_out_dir, **kw)
+
+    @classmethod
+    def from_random_init(cls, arch_name: str = "wavlm_large_s80_md", seed: int = 0, seg_duration: float = 16.0,
+                         segmentation_step: float = 0.1, batch_size: int = 32, min_cluster_size: int = 30,
+                         ahc_threshold: float = 0.70, min_speakers: int = 1, max_speakers: int = 20,
+                         apply_median_filtering: bool = True, classifier_gain: float = 1.0, precision: str = "fp16",
+                         rttm_out_dir: Optional[str] = None, device=None, emb_state_dict=None) -> "DiariZenPipeline":
+        """Seeded random weights of the named architecture (no checkpoint is reachable offline: SURVEY.md 0.8)."""
+        from .archs import init_resnet_state_dict
+        dev = torch.device(device if device is not None else "cuda")
+        arch = get_arch(arch_name)
+        seg = SegmentationModel(arch, init_state_dict(arch, seed, classifier_gain), precision=precision, device=dev)
+        emb = EmbeddingModel(emb_state_dict if emb_state_dict is not None else init_resnet_state_dict(seed), precision=precision, device=dev)
+        config = {
+            "model": {"args": {"wavlm_src": arch_name}},
+            "inference": {"args": {"seg_duration": seg_duration, "segmentation_step": segmentation_step, "batch_size": batch_size,
+                                   "apply_median_filtering": apply_median_filtering}},
+            "clustering": {"args": {"method": "AgglomerativeClustering", "min_speakers": min_speakers, "max_speakers": max_speakers,
+                                    "ahc_criterion": "distance", "ahc_threshold": ahc_threshold, "min_cluster_size": min_cluster_size}},
+        }
+        return cls(None, None, rttm_out_dir=rttm_out_dir, precision=precision, device=dev, _seg=seg, _emb=emb, _config=config)
+
+    # ------------------------------------------------------------------------------------------------
+    def _windows(self, num_samples: int):
+        window = int(math.floor(self.seg_duration * SR))                  # core/inference.py:265
+        step = round(self.segmentation_step * self.seg_duration * SR)     # :266
+        n_full = (num_samples - window) // step + 1 if num_samples >= window else 0
+        has_last = (num_samples < window) or ((num_samples - window) % step > 0)
+        return window, step, n_full + int(has_last)
+
+    def diarize_waveform(self, wav: torch.Tensor) -> Dict[str, Any]:
+        """wav (N,) fp32 -> dict with every intermediate the parity tests compare (rank 0 only under torch.distributed)."""
+        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        rank = dist.get_rank() if dist else 0
+        world = dist.get_world_size() if dist else 1
+        dev = self.device
+        L = self._L
+        Nw = wav.shape[0]
+        window, step, Cn = self._windows(Nw)
+        chunk_step_s = self.segmentation_step * self.seg_duration
+        T = self._segmentation.num_frames(window)
+        S = 4
+        pad_to = (Cn - 1) * step + window
+        wdev = torch.zeros(max(pad_to, Nw), device=dev, dtype=torch.float32)
+        wdev[:Nw] = wav.to(dev, torch.float32)
+        chunks = wdev.as_strided((Cn, window), (step, 1))
+        # window range of this rank
+        per = (Cn + world - 1) // world
+        c0, c1 = min(rank * per, Cn), min((rank + 1) * per, Cn)
+        seg = torch.zeros((per * world, T, S), device=dev, dtype=torch.uint8)
+        bs = self.segmentation_batch_size
+        for a in range(c0, c1, bs):
+            b = min(a + bs, c1)
+            self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg[a:b])
+        if dist:
+            gathered = torch.empty_like(seg)
+            dist.all_gather_into_tensor(gathered, seg[rank * per:(rank + 1) * per].contiguous())
+            seg = gathered
+        seg = seg[:Cn].contiguous()
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        if self.apply_median_filtering:
+            filt = torch.empty_like(seg)
+            _lib.check(L.dz_median_filter(vp(seg.data_ptr()), vp(filt.data_ptr()), Cn, T, S, 11, st))
+            seg = filt
+        # speaker counting
+        starts = np.array([_closest_frame(c * chunk_step_s + 0.5 * FRAME_DURATION) for c in range(Cn)], dtype=np.int32)
+        F = _closest_frame(self.seg_duration + (Cn - 1) * chunk_step_s + 0.5 * FRAME_DURATION) + 1
+        dstart = torch.as_tensor(starts, device=dev)
+        count = torch.empty(F, device=dev, dtype=torch.uint8)
+        maxc = int(self.max_speakers) if self.max_speakers else 255
+        _lib.check(L.dz_speaker_count(vp(seg.data_ptr()), vp(dstart.data_ptr()), Cn, T, S, F, maxc, vp(count.data_ptr()), st))
+        # embedding masks
+        min_num_frames = math.ceil(T * self._embedding.min_num_samples / (self.seg_duration * SR))
+        masks = torch.empty((Cn, S, T), device=dev, dtype=torch.float32)
+        stats = torch.empty((Cn, S, 2), device=dev, dtype=torch.int32)
+        _lib.check(L.dz_embedding_masks(vp(seg.data_ptr()), Cn, T, S, min_num_frames, vp(masks.data_ptr()), vp(stats.data_ptr()), st))
+        # embeddings (chunk crops as the reference computes them: io.py:359-364)
+        e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(Cn)]
+        same = all(e_starts[c] == c * step for c in range(Cn))
+        emb = torch.zeros((per * world, S, 256), device=dev, dtype=torch.float32)
+        ebs = max(1, self.embedding_batch_size // S)
+        for a in range(c0, c1, ebs):
+            b = min(a + ebs, c1)
+            if same:
+                wv = chunks[a:b].contiguous()
+            else:
+                wv = torch.stack([wdev[e_starts[c]:e_starts[c] + window] for c in range(a, b)])
+            emb[a:b] = self._embedding.embed_windows(wv, masks[a:b])
+        if dist:
+            gathered = torch.empty_like(emb)
+            dist.all_gather_into_tensor(gathered, emb[rank * per:(rank + 1) * per].contiguous())
+            emb = gathered
+        if rank != 0:
+            return {}
+        emb_np = emb[:Cn].cpu().numpy()
+        stats_np = stats.cpu().numpy()
+        hard, _, centroids = self.clustering(embeddings=emb_np, segmentations=None, min_clusters=self.min_speakers,
+                                             max_clusters=self.max_speakers,
+                                             frame_stats=(stats_np[..., 0], stats_np[..., 1], T))
+        hard = np.array(hard, dtype=np.int8, copy=True)
+        hard[stats_np[..., 0] == 0] = -2                                   # inactive speakers (inference.py:166-170)
+        K = int(hard.max()) + 1 if hard.size and hard.max() >= 0 else 1
+        maxspf = int(count.max().item())
+        dh = torch.as_tensor(hard, device=dev)
+        Kk = max(K, 1)
+        Kout = max(Kk, maxspf)   # activations are zero padded up to the largest count (diarization.py:222-226)
+        disc = torch.empty((F, Kout), device=dev, dtype=torch.uint8)
+        _lib.check(L.dz_reconstruct(vp(seg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(count.data_ptr()), Cn, T, S,
+                                    Kk, Kout, F, vp(disc.data_ptr()), None, st))
+        discrete = disc.cpu().numpy()
+        out = {"segmentations": seg, "count": count, "embeddings": emb_np, "hard_clusters": hard, "discrete": discrete,
+               "centroids": centroids, "num_chunks": Cn, "num_frames": T}
+        self.last = out
+        return out
+
+    @staticmethod
+    def to_annotation(discrete: np.ndarray, uri: Optional[str]) -> Annotation:
+        """Binarize(onset=0.5, offset=0.5) on a {0,1} matrix (pyannote-audio/pyannote/audio/utils/signal.py:254-317):
+        a region starts at the middle of the first active frame and ends at the middle of the first inactive one."""
+        F, K = discrete.shape
+        ann = Annotation(uri=uri)
+        mid = lambda i: i * FRAME_STEP + 0.5 * FRAME_DURATION
+        for k in range(K):
+            y = discrete[:, k].astype(np.int8)
+            if F == 0:
+                continue
+            d = np.diff(y)
+            on = list(np.where(d == 1)[0] + 1)
+            off = list(np.where(d == -1)[0] + 1)
+            if y[0] == 1:
+                on = [0] + on
+            if y[-1] == 1:
+                off = off + [F - 1]
+            for a, b in zip(on, off):
+                ann[Segment(mid(a), mid(b)), k] = k
+        return ann
+
+    def __call__(self, in_wav, sess_name=None):
+        wav = load_waveform(in_wav)
+        print("Extracting segmentations.")
+        res = self.diarize_waveform(wav)
+        if not res:
+            return None
+        result = self.to_annotation(res["discrete"], sess_name)
+        if self.rttm_out_dir is not None:
+            assert sess_name is not None
+            with open(os.path.join(self.rttm_out_dir, sess_name + ".rttm"), "w") as f:
+                f.write(result.to_rttm())
+        return result

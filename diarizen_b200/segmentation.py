@@ -82,16 +82,20 @@ class SegmentationModel:
             raise ValueError(f"Expected (batch, channel, sample) or (batch, sample), got {tuple(waveforms.shape)}")
         return waveforms.to(self.device, torch.float32).contiguous()
 
-    def hard(self, waveforms: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (log-probs (B,T,11) fp32, multilabel (B,T,4) uint8), both on the device."""
+    def hard(self, waveforms: torch.Tensor, want_logp: bool = True,
+             ml_out: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+        """-> (log-probs (B,T,11) fp32 or None, multilabel (B,T,4) uint8), both on the device.
+        `ml_out`: optional preallocated contiguous uint8 (B,T,4) slice to write the decoding into."""
         w = self._prep(waveforms)
         B, N = w.shape
         T = self.num_frames(N)
-        logp = torch.empty((B, T, self.arch.num_classes), device=self.device, dtype=torch.float32)
-        ml = torch.empty((B, T, NUM_SPEAKERS), device=self.device, dtype=torch.uint8)
+        logp = torch.empty((B, T, self.arch.num_classes), device=self.device, dtype=torch.float32) if want_logp else None
+        ml = ml_out if ml_out is not None else torch.empty((B, T, NUM_SPEAKERS), device=self.device, dtype=torch.uint8)
+        assert ml.is_contiguous() and ml.dtype == torch.uint8 and tuple(ml.shape) == (B, T, NUM_SPEAKERS)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
-            _lib.check(self._L.dz_seg_forward(self._h, C.c_void_p(w.data_ptr()), B, N, C.c_void_p(logp.data_ptr()),
+            _lib.check(self._L.dz_seg_forward(self._h, C.c_void_p(w.data_ptr()), B, N,
+                                              C.c_void_p(logp.data_ptr()) if want_logp else None,
                                               C.c_void_p(ml.data_ptr()), C.c_void_p(st)))
         self._keep = w  # the engine's debug taps replay from this buffer
         return logp, ml

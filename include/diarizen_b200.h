@@ -181,9 +181,10 @@ int dz_speaker_count(const uint8_t* seg_dev, const int32_t* start_dev, int C, in
 int dz_embedding_masks(const uint8_t* seg_dev, int C, int T, int S, int min_frames, float* masks_dev, int32_t* stats_dev,
                        void* stream);
 /* cluster-wise max, overlap-add sum, per-frame top-count selection (speaker_diarization.py:377-425, diarization.py:193-239);
- * discrete [F][max(K,1)] uint8, act (optional) [F][max(K,1)] fp32 */
+ * K clusters, Kout >= K output columns (zero-activation padding when a frame's count exceeds K);
+ * discrete [F][Kout] uint8, act (optional) [F][Kout] fp32 */
 int dz_reconstruct(const uint8_t* seg_dev, const int8_t* hard_dev, const int32_t* start_dev, const uint8_t* count_dev, int C,
-                   int T, int S, int K, int F, uint8_t* discrete_dev, float* act_dev, void* stream);
+                   int T, int S, int K, int Kout, int F, uint8_t* discrete_dev, float* act_dev, void* stream);
 /* full symmetric Euclidean distance matrix [N][N] in float64, bit-compatible with scipy pdist on float64(x) */
 int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream);
 /* scipy linkage(method="centroid") from the distance matrix (destroyed); Z [N-1][4] float64 */

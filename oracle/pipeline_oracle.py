@@ -241,7 +241,10 @@ def reconstruct(segmentations: np.ndarray, hard_clusters: np.ndarray, count: np.
         act = np.pad(act, ((0, 0), (0, maxspf - act.shape[1])))
     F_ = min(act.shape[0], count.shape[0])
     act, cnt = act[:F_], count[:F_]
-    order = np.argsort(-act, axis=-1)
+    # The reference calls np.argsort(-activations) with the default (unstable) kind: which of several speakers with
+    # EQUAL summed activation is kept is platform dependent there (SIMD sort kernels).  The oracle - like the device
+    # kernel - resolves ties towards the lower cluster index.
+    order = np.argsort(-act, axis=-1, kind="stable")
     binary = np.zeros_like(act)
     for t in range(F_):
         for i in range(int(cnt[t, 0])):

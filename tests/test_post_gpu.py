@@ -81,7 +81,7 @@ def test_count_masks_reconstruct(Cn, T, dur):
     dh = torch.as_tensor(hard, device="cuda")
     dc = torch.as_tensor(cnt[:, 0].astype(np.uint8), device="cuda")
     dd = torch.empty((F, K), dtype=torch.uint8, device="cuda")
-    _lib.check(L.dz_reconstruct(vp(dseg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(dc.data_ptr()), Cn, T, S, K, F,
+    _lib.check(L.dz_reconstruct(vp(dseg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(dc.data_ptr()), Cn, T, S, K, K, F,
                                 vp(dd.data_ptr()), None, None))
     got = dd.cpu().numpy().astype(np.float64)
     assert got.shape == disc_ref.shape and np.array_equal(got, disc_ref)
