@@ -31,6 +31,7 @@ from .archs import SegArch, arch_from_reference_config, get_arch, init_state_dic
 from .clustering import AgglomerativeClustering
 from .embedding import EmbeddingModel
 from .segmentation import SegmentationModel
+from .sharding import gather_windows, window_range
 
 SR = 16000
 FRAME_DURATION = 400 / SR    # receptive field of the conv stack (model_wavlm_conformer.py:126-176)
@@ -197,18 +198,13 @@ class DiariZenPipeline:
         wdev[:Nw] = wav.to(dev, torch.float32)
         chunks = wdev.as_strided((Cn, window), (step, 1))
         # window range of this rank
-        per = (Cn + world - 1) // world
-        c0, c1 = min(rank * per, Cn), min((rank + 1) * per, Cn)
-        seg = torch.zeros((per * world, T, S), device=dev, dtype=torch.uint8)
+        c0, c1, per = window_range(Cn, rank, world)
+        seg_local = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
         bs = self.segmentation_batch_size
         for a in range(c0, c1, bs):
             b = min(a + bs, c1)
-            self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg[a:b])
-        if dist:
-            gathered = torch.empty_like(seg)
-            dist.all_gather_into_tensor(gathered, seg[rank * per:(rank + 1) * per].contiguous())
-            seg = gathered
-        seg = seg[:Cn].contiguous()
+            self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg_local[a - c0:b - c0])
+        seg = gather_windows(seg_local, Cn, world).contiguous()
         st = vp(torch.cuda.current_stream().cuda_stream)
         if self.apply_median_filtering:
             filt = torch.empty_like(seg)
@@ -229,7 +225,7 @@ class DiariZenPipeline:
         # embeddings (chunk crops as the reference computes them: io.py:359-364)
         e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(Cn)]
         same = all(e_starts[c] == c * step for c in range(Cn))
-        emb = torch.zeros((per * world, S, 256), device=dev, dtype=torch.float32)
+        emb_local = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
         ebs = max(1, self.embedding_batch_size // S)
         for a in range(c0, c1, ebs):
             b = min(a + ebs, c1)
@@ -237,14 +233,11 @@ class DiariZenPipeline:
                 wv = chunks[a:b].contiguous()
             else:
                 wv = torch.stack([wdev[e_starts[c]:e_starts[c] + window] for c in range(a, b)])
-            emb[a:b] = self._embedding.embed_windows(wv, masks[a:b])
-        if dist:
-            gathered = torch.empty_like(emb)
-            dist.all_gather_into_tensor(gathered, emb[rank * per:(rank + 1) * per].contiguous())
-            emb = gathered
+            emb_local[a - c0:b - c0] = self._embedding.embed_windows(wv, masks[a:b])
+        emb = gather_windows(emb_local, Cn, world)          # the single data-path collective (NCCL all-gather)
         if rank != 0:
             return {}
-        emb_np = emb[:Cn].cpu().numpy()
+        emb_np = emb.cpu().numpy()
         stats_np = stats.cpu().numpy()
         hard, _, centroids = self.clustering(embeddings=emb_np, segmentations=None, min_clusters=self.min_speakers,
                                              max_clusters=self.max_speakers,

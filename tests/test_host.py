@@ -1,0 +1,119 @@
+"""Host-side logic that needs no GPU: C ABI exports, architecture tables, result types, waveform decoding,
+the relative-position bucket function, and the window sharding / gather used for N > 1 (gloo, world_size 2)."""
+import io
+import os
+import re
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from diarizen_b200 import _lib
+from diarizen_b200.annotation import Annotation, Segment
+from diarizen_b200.archs import ARCHS, get_arch, param_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "diarizen_b200.h")).read()
+    declared = set(re.findall(r"\b(dz_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dz_gemm_desc", "dz_attn_args", "dz_seg_arch"}
+    L = _lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"not exported: {missing}"
+    assert set(_lib.EXPORTS) <= declared | {"dz_relpos_bucket"}
+    assert L.dz_abi_version() == 1
+
+
+def test_relpos_bucket_matches_oracle():
+    from oracle.seg_oracle import rel_pos_bucket
+    L = _lib.lib()
+    d = torch.arange(-1700, 1701)
+    mine = torch.tensor([L.dz_relpos_bucket(int(x)) for x in d])
+    assert torch.equal(mine, rel_pos_bucket(d))
+
+
+def test_no_cuda_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from diarizen_b200.segmentation import SegmentationModel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SegmentationModel.random_init("tiny_base")
+
+
+def test_num_frames_table():
+    a = get_arch("wavlm_large_s80_md")
+    assert [a.num_frames(n) for n in (16000, 80000, 128000, 256000)] == [49, 249, 399, 799]   # model_wavlm_conformer.py:113-124
+    assert a.conv_frames(256000) == [51199, 25599, 12799, 6399, 3199, 1599, 799]
+
+
+def test_param_shapes_count_parameters():
+    # 94.38 M params for the unpruned base encoder stack, 63.10 M for large-s80
+    def wavlm_params(name):
+        return sum(int(np.prod(s)) for k, s in param_shapes(get_arch(name)).items() if k.startswith("wavlm_model."))
+    assert abs(wavlm_params("wavlm_base") / 1e6 - 94.38) < 0.05
+    assert abs(wavlm_params("wavlm_large_s80_md") / 1e6 - 63.10) < 0.05
+    for n in ARCHS:
+        assert get_arch(n.upper()).name == n
+    with pytest.raises(ValueError):
+        get_arch("nope")
+
+
+def test_annotation_protocol():
+    ann = Annotation(uri="sess")
+    ann[Segment(1.0, 2.5), 1] = 1
+    ann[Segment(0.0, 2.7), 0] = 0
+    ann[Segment(1.0, 2.0), 0] = 0
+    tracks = list(ann.itertracks(yield_label=True))
+    assert [t[0] for t in tracks] == [Segment(0.0, 2.7), Segment(1.0, 2.0), Segment(1.0, 2.5)]
+    assert ann.to_rttm().splitlines()[0] == "SPEAKER sess 1 0.000 2.700 <NA> <NA> 0 <NA> <NA>"
+    assert Annotation().to_rttm() == "" and ann.labels() == [0, 1]
+
+
+def test_load_waveform_wav_bytes_and_dict(tmp_path):
+    from diarizen_b200.pipeline import load_waveform
+    x = (np.sin(np.arange(1600) / 10) * 20000).astype("<i2")
+    stereo = np.stack([x, -x], axis=1)
+    p = tmp_path / "a.wav"
+    for target in (str(p), io.BytesIO()):
+        with wave.open(target, "wb") as f:
+            f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000); f.writeframes(stereo.tobytes())
+        if isinstance(target, io.BytesIO):
+            target.seek(0)
+        w = load_waveform(target)
+        assert w.shape == (1600,) and torch.allclose(w, torch.from_numpy(x.astype(np.float32) / 32768.0))   # channel 0
+    assert load_waveform({"waveform": torch.zeros(1, 7), "sample_rate": 16000}).shape == (7,)
+    with pytest.raises(TypeError):
+        load_waveform(3)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diarizen_b200.sharding import gather_windows, window_range
+    Cn, T = 11, 7
+    a, b, per = window_range(Cn, rank, world)
+    local = torch.zeros((per, T), dtype=torch.uint8)
+    for c in range(a, b):
+        local[c - a] = c + 1
+    full = gather_windows(local, Cn, world)
+    q.put((rank, full.numpy()))
+    dist.destroy_process_group()
+
+
+def test_window_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    expect = np.repeat(np.arange(1, 12, dtype=np.uint8)[:, None], 7, axis=1)
+    assert np.array_equal(outs[0], expect) and np.array_equal(outs[1], expect)
