@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -145,6 +146,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "pipeline":
+        return run_reference_pipeline(args)
     N = int(args.seconds * SR)
     per_step = args.ref_windows
     from diarizen_b200.archs import get_arch, init_state_dict
@@ -172,6 +175,46 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def run_reference_pipeline(args):
+    """Reference arm for the pipeline workload: per step, the oracle port of both network forwards on a bounded number of
+    windows (the embedding trunk executed once per (window, speaker) pair as the reference does); stream rate = windows x
+    step / time.  Clustering is NOT included in this arm's timed region (it is in cpu_baseline of the main arm)."""
+    from diarizen_b200.archs import get_arch, init_resnet_state_dict, init_state_dict
+    from oracle.emb_oracle import emb_forward
+    from oracle.seg_oracle import seg_forward
+    dur = args.seconds
+    N = int(dur * SR)
+    nw = max(1, args.ref_windows // 8)
+    cores = pick_threads(args.arch, N)
+    a = get_arch(args.arch)
+    sd, esd = init_state_dict(a, 0), init_resnet_state_dict(0)
+    wav = synth_wav(nw, N)
+    T = a.num_frames(N)
+    masks = torch.ones(nw, 1, T)
+
+    def step():
+        seg_forward(a, sd, wav)
+        for _ in range(4):
+            emb_forward(esd, wav, masks)
+    for _ in range(max(1, args.warmup)):
+        seg_forward(a, sd, wav[:1]); emb_forward(esd, wav[:1], masks[:1])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.steps * nw * dur * 0.1 / dt
+    sample = (f"{nw} windows x {dur:g} s per step ({args.steps} steps): oracle port of Model.forward + 4 ResNet34 passes per window "
+              f"(trunk per (window, speaker) pair); stream seconds = windows x {dur * 0.1:g} s step; clustering excluded")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.arch} full pipeline, {dur:g} s windows / {dur * 0.1:g} s step (BASELINE.json configs[2])", "arch": args.arch,
+                      "window_s": dur, "windows_per_step": nw},
+           "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
 def workload_name(args):
     return f"{args.arch} segmentation forward, {args.seconds:g} s / 16 kHz windows, batch {args.batch} per GPU (BASELINE.json configs[1])"
 
@@ -189,22 +232,218 @@ def classify(step_name: str) -> str:
     return "gemm"
 
 
+def synth_meeting(seconds: float, seed: int = 0) -> torch.Tensor:
+    """Synthetic 16 kHz mono 'meeting': four spectrally distinct noise sources gated on/off in turns (seeded)."""
+    g = torch.Generator().manual_seed(seed)
+    n = int(seconds * SR)
+    wav = torch.zeros(n)
+    t = torch.arange(n, dtype=torch.float32) / SR
+    for s, f0 in enumerate((150.0, 260.0, 410.0, 600.0)):
+        src = 0.04 * torch.randn(n, generator=g) + 0.08 * torch.sin(2 * math.pi * f0 * t) * (1 + 0.3 * torch.sin(2 * math.pi * (1.5 + s) * t))
+        edges = torch.cumsum(torch.randint(SR // 2, 6 * SR, (int(seconds / 1.5) + 8,), generator=g), 0)
+        edges = edges[edges < n]
+        gate = torch.zeros(n)
+        on = bool(s % 2)
+        prev = 0
+        for e in edges.tolist() + [n]:
+            if on:
+                gate[prev:e] = 1.0
+            on = not on if torch.rand(1, generator=g).item() < 0.8 else on
+            prev = e
+        wav += src * gate
+    return wav.clamp_(-1.0, 1.0)
+
+
+def pipeline_cpu_rate(arch_name: str, seconds_per_window: float, step_s: float, n_seg: int, n_emb: int, emb_np=None, seg_np=None):
+    """Reference algorithm on the host cores, bounded sample: oracle segmentation forward on n_seg windows, the embedding
+    forward on n_emb windows executed as the reference does (trunk once per (window, speaker) pair: 4x), scipy clustering on
+    the embeddings the GPU run produced.  -> (stream audio-s/s, cores, description)."""
+    from diarizen_b200.archs import get_arch, init_resnet_state_dict, init_state_dict
+    from oracle.emb_oracle import emb_forward
+    from oracle.seg_oracle import seg_forward
+    N = int(seconds_per_window * SR)
+    cores = pick_threads(arch_name, N)
+    a = get_arch(arch_name)
+    sd = init_state_dict(a, 0)
+    esd = init_resnet_state_dict(0)
+    wav = synth_wav(max(n_seg, n_emb), N)
+    T = a.num_frames(N)
+    seg_forward(a, sd, wav[:1])
+    t0 = time.perf_counter()
+    seg_forward(a, sd, wav[:n_seg])
+    t_seg = (time.perf_counter() - t0) / n_seg
+    masks = torch.ones(n_emb, 1, T)
+    emb_forward(esd, wav[:1], masks[:1])
+    t0 = time.perf_counter()
+    for _ in range(4):                       # speaker_diarization.py:295-322: one forward per (chunk, speaker)
+        emb_forward(esd, wav[:n_emb], masks)
+    t_emb = (time.perf_counter() - t0) / n_emb
+    t_clu = 0.0
+    n_train = 0
+    if emb_np is not None and seg_np is not None:
+        from oracle import pipeline_oracle as po
+        t0 = time.perf_counter()
+        try:
+            po.cluster_call(emb_np, seg_np, 0.70, 30, 1, 20)
+        except Exception:
+            pass
+        t_clu = time.perf_counter() - t0
+        n_train = int(emb_np.shape[0] * emb_np.shape[1])
+    per_window = t_seg + t_emb
+    return per_window, t_clu, cores, (f"{n_seg} seg windows + {n_emb} windows x 4 embedding passes x {seconds_per_window:g} s, fp32 torch oracle port; "
+                                      f"scipy centroid clustering of {n_train} embeddings: {t_clu:.1f} s; {per_window * 1e3:.0f} ms CPU per window")
+
+
+def run_pipeline_bench(args, world, rank, local, dist):
+    from diarizen_b200.pipeline import DiariZenPipeline
+    seconds = args.minutes * 60.0
+    dur = args.seconds
+    pipe = DiariZenPipeline.from_random_init(args.arch, seed=0, seg_duration=dur, batch_size=args.batch, classifier_gain=40.0,
+                                             precision=args.precision)
+    recs = [synth_meeting(seconds, seed=100 + i) for i in range(1)]
+    wav_host = recs[0].pin_memory()
+    wav_dev = wav_host.cuda()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # N ranks process N recordings' worth of audio (weak scaling); every recording is window-sharded over all ranks
+    n_rec = world
+    for _ in range(args.warmup):
+        pipe.diarize_waveform(wav_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        for _r in range(n_rec):
+            res = pipe.diarize_waveform(wav_dev)
+            if res:
+                pipe.to_annotation(res["discrete"], "bench")
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # end to end: host waveform in, Annotation out
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _r in range(n_rec):
+            ann = pipe({"waveform": wav_host[None], "sample_rate": SR}, sess_name="bench")
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return
+    audio_per_step = n_rec * seconds
+    last = pipe.last
+    Cn, T = last["num_chunks"], last["num_frames"]
+    peaks = measured_peaks()
+    # per-class device time of one batch of each network (CUDA events per launch), scaled by the number of batches
+    window = int(dur * SR)
+    bsz = args.batch
+    wb = wav_dev[: window].repeat(bsz, 1).contiguous()
+    seg_prof = pipe._segmentation.profile(wb)
+    seg_prof = pipe._segmentation.profile(wb)
+    ebs = max(1, bsz // 4)
+    pipe._embedding.embed_windows(wb[:ebs], torch.ones(ebs, 4, T, device="cuda"))
+    emb_prof = pipe._embedding.profile()
+    n_seg_b, n_emb_b = Cn / bsz / world, Cn / ebs / world
+    classes = {}
+    for name, pms, fl, by in seg_prof:
+        c = classes.setdefault("seg:" + classify(name), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        c["ms"] += pms * n_seg_b; c["flops"] += fl * n_seg_b; c["bytes"] += by * n_seg_b; c["n"] += 1
+    for name, pms, fl in emb_prof:
+        cls = "emb:conv_gemm" if ("conv" in name and name != "conv1") or name.endswith("_sc") or name == "seg_1" else "emb:other"
+        c = classes.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        c["ms"] += pms * n_emb_b; c["flops"] += fl * n_emb_b; c["n"] += 1
+    total_ms = sum(c["ms"] for c in classes.values())
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    d = classes[dom]
+    if d["flops"] > 0:
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (" + dom + ")", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tensor"], "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)",
+                "share_of_network_time": d["ms"] / total_ms}
+    else:
+        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "traffic": None, "peak_source": peaks["src"], "share_of_network_time": d["ms"] / total_ms}
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            roof["traffic"] = json.load(f).get("gemm_tc_kernel")
+    except Exception:
+        pass
+    breakdown = {k: {"ms_per_recording": round(v["ms"], 2), "share": round(v["ms"] / total_ms, 4),
+                     "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
+                 for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+    breakdown["networks_total_ms"] = round(total_ms, 1)
+    breakdown["whole_recording_ms"] = round(ms / args.steps / n_rec, 1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        seg_np = last["segmentations"].cpu().numpy().astype("float32")
+        per_w, t_clu, cores, desc = pipeline_cpu_rate(args.arch, dur, dur * 0.1, args.cpu_windows, max(1, args.cpu_windows // 2),
+                                                      last["embeddings"], seg_np)
+        cpu = {"value": seconds / (Cn * per_w + t_clu), "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc}
+    launches = (pipe._segmentation.last_launches * math.ceil(Cn / bsz / world) + pipe._embedding.last_launches * math.ceil(Cn / ebs / world) + 8) * n_rec * args.steps
+    out = {
+        "metric": METRIC, "value": audio_per_step * args.steps / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": {"fp16": "fp16 operands, fp32 accumulate", "bf16": "bf16 operands, fp32 accumulate", "bf16x3": "bf16x3 split (fp32-class)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"{args.arch} full pipeline (segmentation + ResNet34 embeddings + centroid AHC + reconstruction), "
+                               f"{args.minutes:g} min synthetic 16 kHz meeting per GPU, {dur:g} s windows / {dur * 0.1:g} s step (BASELINE.json configs[2])",
+                   "arch": args.arch, "window_s": dur, "windows_per_recording": Cn, "batch": bsz,
+                   "recordings_per_step": n_rec,
+                   "parallelism": f"each recording window-sharded over {world} rank(s), one NCCL all-gather of segmentations + embeddings, clustering on rank 0",
+                   "clusters_found": int(last["hard_clusters"].max()) + 1,
+                   "l2": "the recording (230 MB/h) and per-batch activations (GBs) exceed the 126 MB L2; no explicit flush"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": audio_per_step * args.steps / (ms_e2e * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(n_rec * wav_host.numel() * 4),
+                "d2h_bytes_per_step": int(n_rec * (last["embeddings"].nbytes + last["discrete"].nbytes + last["hard_clusters"].nbytes)),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "breakdown": breakdown,
+    }
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--arch", default="wavlm_base_s80_md")
-    ap.add_argument("--seconds", type=float, default=5.0)
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "seg"],
+                    help="pipeline = BASELINE.json configs[2] (large-s80 full pipeline, the metric's configuration); seg = configs[1]")
+    ap.add_argument("--arch", default=None)
+    ap.add_argument("--seconds", type=float, default=None, help="window length")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--minutes", type=float, default=60.0, help="recording length of the pipeline workload")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "bf16x3"])
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (name, ms, flops, bytes) as JSON")
     ap.add_argument("--attn", default=os.environ.get("DZ_ATTN", "tc"), choices=["tc", "simt"])
     ap.add_argument("--ref-windows", type=int, default=16)
-    ap.add_argument("--cpu-windows", type=int, default=32)
+    ap.add_argument("--cpu-windows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "pipeline":
+        args.arch = args.arch or "wavlm_large_s80_md"; args.seconds = args.seconds or 16.0; args.batch = args.batch or 32
+        args.cpu_windows = args.cpu_windows or 4
+    else:
+        args.arch = args.arch or "wavlm_base_s80_md"; args.seconds = args.seconds or 5.0; args.batch = args.batch or 256
+        args.cpu_windows = args.cpu_windows or 32
+    args.steps = args.steps or (3 if args.workload == "pipeline" else 10)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -222,6 +461,13 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if args.workload == "pipeline":
+        run_pipeline_bench(args, world, rank, local, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     from diarizen_b200.segmentation import SegmentationModel
     N = int(args.seconds * SR)
