@@ -63,78 +63,85 @@ DZ_DEVINL TileCoord decode_tile(const GemmDesc& d, int tile, int mt, int nt, int
 
 static constexpr int PATCH_LD = 36;  // floats per patch row: 16-byte aligned rows, conflict-free float4 access
 
-template <int ACT>
-DZ_DEVINL float act_t(float x) {
-  if (ACT == 1) return gelu_erf(x);
-  if (ACT == 2) return __fdividef(x, 1.0f + __expf(-x));
-  if (ACT == 3) return fmaxf(x, 0.0f);
-  return x;
+DZ_DEVINL float4 act4(float4 v, int act) {
+  // one copy of each activation in the instruction stream (the epilogue is instruction-cache sensitive)
+  switch (act) {
+    case 1: v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); break;
+    case 2:
+      v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+      v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+      break;
+    case 3: v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); break;
+    default: break;
+  }
+  return v;
+}
+
+DZ_DEVINL float4 ld_res16(const bf16* rp, long long plane, bool two, int fp16) {
+  const uint2 hw = *reinterpret_cast<const uint2*>(rp);
+  float4 q;
+  q.x = from16(__ushort_as_bfloat16((unsigned short)(hw.x & 0xffff)), fp16);
+  q.y = from16(__ushort_as_bfloat16((unsigned short)(hw.x >> 16)), fp16);
+  q.z = from16(__ushort_as_bfloat16((unsigned short)(hw.y & 0xffff)), fp16);
+  q.w = from16(__ushort_as_bfloat16((unsigned short)(hw.y >> 16)), fp16);
+  if (two) {
+    const uint2 lw = *reinterpret_cast<const uint2*>(rp + plane);
+    q.x += from16(__ushort_as_bfloat16((unsigned short)(lw.x & 0xffff)), fp16);
+    q.y += from16(__ushort_as_bfloat16((unsigned short)(lw.x >> 16)), fp16);
+    q.z += from16(__ushort_as_bfloat16((unsigned short)(lw.y & 0xffff)), fp16);
+    q.w += from16(__ushort_as_bfloat16((unsigned short)(lw.y >> 16)), fp16);
+  }
+  return q;
 }
 
 // Full 32-column chunk (all columns valid and row-major): lane = (row-in-group of 4, 4-column slot); one warp
-// instruction covers 4 rows x 128 B.  The residual rows of the whole chunk are fetched up front (8 x 16 B per lane).
-template <int ACT>
+// instruction covers 4 rows x 128 B.  The fp32 residual rows of the whole chunk are fetched up front (8 x 16 B per lane
+// in flight); the row loop itself is kept rolled: code size matters more than loop overhead here.
 DZ_DEVINL void epi_rows_fast(const GemmDesc& d, const TileCoord& tc, const float* patch, int lane, int mrow0, int nrows,
                              int ncol0) {
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   const int gcol = tc.g * d.group_cols + ncol0 + c4;
-  float4 res[8];
-  const bool has_res = d.residual != nullptr || d.res16 != nullptr;
   const int fp16 = d.fp16;
-  if (d.residual != nullptr) {
-    const float* resp = d.residual + (long long)tc.b * d.res_bstride + (long long)mrow0 * d.ldr + gcol;
+  const bool two = d.out_planes > 1;
+  float4 res[8];
+  const float* resp = d.residual ? d.residual + (long long)tc.b * d.res_bstride + (long long)mrow0 * d.ldr + gcol : nullptr;
+  if (resp != nullptr) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = 4 * i + rsub;
       res[i] = (r < nrows) ? *reinterpret_cast<const float4*>(resp + r * d.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else if (d.res16 != nullptr) {
-    const bf16* rp = (const bf16*)d.res16 + (long long)tc.b * d.res16_bstride + (long long)(mrow0 + d.res16_row_off) * d.ldr16 + gcol;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + rsub;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nrows) {
-        const uint2 hw = *reinterpret_cast<const uint2*>(rp + r * d.ldr16);
-        q.x = from16(__ushort_as_bfloat16((unsigned short)(hw.x & 0xffff)), fp16);
-        q.y = from16(__ushort_as_bfloat16((unsigned short)(hw.x >> 16)), fp16);
-        q.z = from16(__ushort_as_bfloat16((unsigned short)(hw.y & 0xffff)), fp16);
-        q.w = from16(__ushort_as_bfloat16((unsigned short)(hw.y >> 16)), fp16);
-        if (d.out_planes > 1) {
-          const uint2 lw = *reinterpret_cast<const uint2*>(rp + d.res16_plane + r * d.ldr16);
-          q.x += from16(__ushort_as_bfloat16((unsigned short)(lw.x & 0xffff)), fp16);
-          q.y += from16(__ushort_as_bfloat16((unsigned short)(lw.x >> 16)), fp16);
-          q.z += from16(__ushort_as_bfloat16((unsigned short)(lw.y & 0xffff)), fp16);
-          q.w += from16(__ushort_as_bfloat16((unsigned short)(lw.y >> 16)), fp16);
-        }
-      }
-      res[i] = q;
-    }
   }
+  const bf16* r16 = d.res16 ? (const bf16*)d.res16 + (long long)tc.b * d.res16_bstride +
+                                  (long long)(mrow0 + d.res16_row_off) * d.ldr16 + gcol
+                            : nullptr;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if (d.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(d.bias + gcol));
   float* outp = d.out_f32 ? d.out_f32 + (long long)tc.b * d.of_bstride + (long long)mrow0 * d.ldo + gcol : nullptr;
   bf16* bfp = d.out_bf ? (bf16*)d.out_bf + (long long)tc.b * d.ob_bstride + (long long)(mrow0 + d.out_row_off) * d.ldob + gcol
                        : nullptr;
   const float alpha = d.alpha;
-  const bool two = d.out_planes > 1;
+  const int act = d.act;
   const bool after = d.act_after_res != 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + rsub;
-    if (r >= nrows) continue;
+    if (r >= nrows) break;
     float4 v = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + c4);
-    if (after) {
-      v.x = alpha * (v.x + bias.x); v.y = alpha * (v.y + bias.y); v.z = alpha * (v.z + bias.z); v.w = alpha * (v.w + bias.w);
-      if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-      v.x = act_t<ACT>(v.x); v.y = act_t<ACT>(v.y); v.z = act_t<ACT>(v.z); v.w = act_t<ACT>(v.w);
-    } else {
-      v.x = alpha * act_t<ACT>(v.x + bias.x);
-      v.y = alpha * act_t<ACT>(v.y + bias.y);
-      v.z = alpha * act_t<ACT>(v.z + bias.z);
-      v.w = alpha * act_t<ACT>(v.w + bias.w);
-      if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+    if (!after) v = act4(v, act);
+    v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+    if (resp != nullptr) {
+      // res[] is indexed with a loop-variant subscript: keep it in registers through a uniform select chain
+      float4 q = res[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) if (i == j) q = res[j];
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    } else if (r16 != nullptr) {
+      const float4 q = ld_res16(r16 + r * d.ldr16, d.res16_plane, two, fp16);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
+    if (after) v = act4(v, act);
     if (outp != nullptr) *reinterpret_cast<float4*>(outp + r * d.ldo) = v;
     if (bfp != nullptr) {
       bf16 h0, h1, h2, h3, l0, l1, l2, l3;
@@ -312,49 +319,42 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
         tmem_ld_32x32(tmem_acc + (uint32_t)c, r);
         tmem_ld_wait();
         const int ncol0 = tc.n0 + c;
-        // transposed outputs (v^T): thread <-> row, coalesced along rows straight from registers
-        if (d.out_t != nullptr && ncol0 + 32 > d.tr_col0) {
-          const int m = mrow0 + lane;
-          if (m < d.M) {
-            const int sb = m / d.seq_len, st = m - sb * d.seq_len;
-            bf16* tp = (bf16*)d.out_t + (long long)sb * d.ot_bstride + st;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = ncol0 + j;
-              if (n >= d.tr_col0 && n < d.N) {
-                float v = __uint_as_float(r[j]);
-                if (d.bias != nullptr) v += __ldg(d.bias + tc.g * d.group_cols + n);
-                v = d.alpha * apply_act(v, d.act);
-                bf16 h, l;
-                split_bf16(v, h, l, d.fp16);
-                bf16* q = tp + (long long)(n - d.tr_col0) * d.ldt;
-                *q = h;
-                if (d.out_planes > 1) q[d.ot_plane] = l;
-              }
-            }
-          }
-        }
-        // row-major outputs: 32x32 transpose through the warp's private patch, then 4 rows x 128 B per instruction
-        if (ncol0 < max(rm_cols, d.zero_pad_to) || d.out_f32 != nullptr) {
+        // 32x32 transpose buffer: thread (= accumulator row) writes its 32 columns
+        {
           float4* prow = reinterpret_cast<float4*>(patch + lane * PATCH_LD);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             prow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                   __uint_as_float(r[4 * j + 3]));
-          __syncwarp();
-          const int nrows = min(32, d.M - mrow0);
-          if (ncol0 + 32 <= rm_cols) {
-            switch (d.act) {
-              case 1: epi_rows_fast<1>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
-              case 2: epi_rows_fast<2>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
-              case 3: epi_rows_fast<3>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
-              default: epi_rows_fast<0>(d, tc, patch, lane, mrow0, nrows, ncol0); break;
-            }
-          } else {
-            epi_rows_edge(d, tc, patch, lane, mrow0, nrows, ncol0, rm_cols);
-          }
-          __syncwarp();
         }
+        __syncwarp();
+        const int nrows = min(32, d.M - mrow0);
+        // transposed outputs (v^T): lane <-> row so that consecutive lanes write consecutive frames of one feature
+        if (d.out_t != nullptr && ncol0 + 32 > d.tr_col0 && lane < nrows) {
+          const int m = mrow0 + lane;
+          const int sb = m / d.seq_len, st = m - sb * d.seq_len;
+          bf16* tp = (bf16*)d.out_t + (long long)sb * d.ot_bstride + st;
+          const float* prow = patch + lane * PATCH_LD;
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            const int n = ncol0 + j;
+            if (n < d.tr_col0 || n >= d.N) continue;
+            float v = prow[j];
+            if (d.bias != nullptr) v += __ldg(d.bias + tc.g * d.group_cols + n);
+            v = d.alpha * apply_act(v, d.act);
+            bf16 h, l;
+            split_bf16(v, h, l, d.fp16);
+            bf16* q = tp + (long long)(n - d.tr_col0) * d.ldt;
+            *q = h;
+            if (d.out_planes > 1) q[d.ot_plane] = l;
+          }
+        }
+        // row-major outputs: 4 rows x 128 B per warp instruction
+        if (ncol0 < max(rm_cols, d.zero_pad_to) || d.out_f32 != nullptr) {
+          if (ncol0 + 32 <= rm_cols) epi_rows_fast(d, tc, patch, lane, mrow0, nrows, ncol0);
+          else epi_rows_edge(d, tc, patch, lane, mrow0, nrows, ncol0, rm_cols);
+        }
+        __syncwarp();
       }
       // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
       tc_fence_before();
