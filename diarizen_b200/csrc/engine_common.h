@@ -110,7 +110,7 @@ inline cudaError_t make_weight(Weight& W, const float* w, int groups, int N, int
   e = cudaMemcpy(W.w.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   if (bias != nullptr) {
-    std::vector<float> bb((size_t)rup(nbias, 32) + 32, 0.f);
+    std::vector<float> bb((size_t)rup(nbias, 64) + 64, 0.f);
     for (int i = 0; i < nbias; ++i) bb[i] = bias[i];
     e = upload_vec(W.bias, bb);
   }

@@ -17,6 +17,7 @@
 // This kernel replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv1d on the reference hot path
 // (reference: diarizen/models/module/wav2vec2/components.py:119 conv1d, :305-306 projection, :374 pos-conv,
 //  :455-480 q/k/v/out projections, :805-814 FFN; diarizen/models/module/conformer.py:116-214).
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -368,6 +369,302 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
   }
 }
 
+// ================================================================================================
+// TMA-epilogue variant.  Same producer / MMA warps; 4 epilogue warps (one per TMEM lane quarter) work in the
+// accumulator's native thread-per-row layout: tcgen05.ld 16 columns -> bias / activation / residual in registers ->
+// 16-byte stores into a 128-byte-swizzled shared-memory patch -> one cp.async.bulk.tensor store per 32-row x 128-byte
+// sub-tile.  Residual sub-tiles (fp32, or 16-bit planes for the ResNet shortcut) arrive through TMA loads issued one
+// span ahead.  No per-element global address arithmetic, no transposition; out-of-range rows / columns are clipped by
+// the tensor maps.  mode 0: fp32 output (span = 32 columns); mode 1: 16-bit plane output (span = 64 columns).
+// ================================================================================================
+struct EpiMaps { CUtensorMap res, res_lo, out, out_lo; };
+static constexpr int NUM_EPI2 = 8;                       // two epilogue warps per TMEM lane quarter, alternating spans
+static constexpr int NUM_THREADS2 = 64 + 32 * NUM_EPI2;
+static constexpr int PATCH2_BYTES = 8192;                // per epilogue warp: 2 x 4 KB (double buffer, or hi|lo planes)
+
+template <int BN>
+struct TcCfg2 {
+  static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
+  static constexpr int NSTAGE = (BN == 256) ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES + NUM_EPI2 * PATCH2_BYTES + 1024 + 256;
+};
+
+DZ_DEVINL float4 unpack4(uint2 w, int fp16) {
+  float4 q;
+  q.x = from16(__ushort_as_bfloat16((unsigned short)(w.x & 0xffff)), fp16);
+  q.y = from16(__ushort_as_bfloat16((unsigned short)(w.x >> 16)), fp16);
+  q.z = from16(__ushort_as_bfloat16((unsigned short)(w.y & 0xffff)), fp16);
+  q.w = from16(__ushort_as_bfloat16((unsigned short)(w.y >> 16)), fp16);
+  return q;
+}
+
+// bias + pre-residual activation + scale on 32 accumulator columns held in registers (one code block per activation)
+template <int ACT>
+DZ_DEVINL void epi_math32(float (&v)[32], const float* __restrict__ bias, float alpha) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = v[j];
+    if (ACT == 1) x = gelu_erf(x);
+    if (ACT == 2) x = __fdividef(x, 1.0f + __expf(-x));
+    if (ACT == 3) x = fmaxf(x, 0.f);
+    v[j] = x * alpha;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiMaps em, const GemmDesc d, const int a_rank5,
+                   const int mt, const int nt, const int ntiles, const int mode) {
+  using C = TcCfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* patches = smem + C::NSTAGE * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(patches + NUM_EPI2 * PATCH2_BYTES);
+  uint64_t* empty_bar = full_bar + C::NSTAGE;
+  uint64_t* tmem_full = empty_bar + C::NSTAGE;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* res_bar = tmem_empty + 2;            // [8 warps][2 buffers]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * NUM_EPI2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool conv2d = d.conv_runs > 0;
+  const int kbpr = conv2d ? (d.conv_run_len + BK - 1) / BK : 0;
+  const int kblocks = conv2d ? d.conv_runs * kbpr : (d.K + BK - 1) / BK;
+  const int iters = kblocks * d.npass;
+  constexpr int A_BYTES = BM * BK * 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], NUM_EPI2); mbar_init(&tmem_empty[1], NUM_EPI2);
+    for (int i = 0; i < 2 * NUM_EPI2; ++i) mbar_init(&res_bar[i], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.b[0]); tma_prefetch_desc(&em.out);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gi = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+        for (int it = 0; it < iters; ++it, ++gi) {
+          const int s = gi % C::NSTAGE;
+          const uint32_t ph = (gi / C::NSTAGE) & 1;
+          const int pass = it / kblocks;
+          const int kb = it - pass * kblocks;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          const CUtensorMap* ma = &maps.a[pass == 1 ? 1 : 0];
+          const CUtensorMap* mb = &maps.b[pass == 2 ? 1 : 0];
+          if (conv2d) {
+            const int run = kb / kbpr, kbr = kb - run * kbpr;
+            const int img = tc.b / d.conv_Ho, ho = tc.b - img * d.conv_Ho;
+            tma_load_4d(sa, ma, &full_bar[s], d.conv_x0 + kbr * BK, tc.m0, d.conv_hs * ho + d.conv_h0 + run, img);
+          } else if (a_rank5) {
+            tma_load_5d(sa, ma, &full_bar[s], 0, kb, tc.m0, tc.g, tc.b);
+          } else {
+            tma_load_3d(sa, ma, &full_bar[s], kb * BK, tc.m0, tc.b);
+          }
+          tma_load_3d(sb, mb, &full_bar[s], kb * BK, tc.n0, tc.g);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int gi = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+        const int n_valid = min(BN, d.N - tc.n0);
+        const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)((n_valid + 15) & ~15), d.fp16);
+        const int acc = tcount & 1;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+        mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int it = 0; it < iters; ++it, ++gi) {
+          const int s = gi % C::NSTAGE;
+          const uint32_t ph = (gi / C::NSTAGE) & 1;
+          const int kb = it % kblocks;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const int krem = conv2d ? d.conv_run_len - (kb % kbpr) * BK : d.K - kb * BK;
+          const int ksteps = krem >= BK ? (BK / 16) : ((krem + 15) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_acc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: thread <-> accumulator row; warps (quad, par) take spans s = par (mod 2) ----------------
+    const int ew = warp - 2;          // 0..7
+    const int quad = warp & 3;        // TMEM lane quarter
+    const int par = ew >> 2;          // span parity served by this warp
+    uint8_t* pw = patches + ew * PATCH2_BYTES;
+    uint64_t* rb = res_bar + ew * 2;
+    const int SW = mode ? 64 : 32;
+    const bool two = d.out_planes > 1;
+    const bool has_res = mode ? (d.res16 != nullptr) : (d.residual != nullptr);
+    const bool dbl = !(mode && two);  // double-buffered patches unless both planes are needed (hi | lo share the 8 KB)
+    const int fp16 = d.fp16;
+    const int sw = lane & 7;
+    const bool relu_after = d.act_after_res && d.act == 3;
+    const int pre_act = d.act_after_res ? 0 : d.act;
+    const uint32_t res_bytes = (mode && two) ? 8192u : 4096u;
+    const int ncols_out = mode ? max(d.N, d.zero_pad_to) : d.N;
+    uint32_t sc = 0;               // spans processed by this warp
+    uint32_t use0 = 0, use1 = 0;   // residual loads consumed per buffer (mbarrier phase)
+    int tcount = 0;
+    auto issue_res = [&](const TileCoord& tc, int col0, int buf) {
+      uint8_t* dst = pw + (dbl ? buf * 4096 : 0);
+      mbar_expect_tx(&rb[buf], res_bytes);
+      const int row0 = tc.m0 + quad * 32 + (mode ? d.res16_row_off : 0);
+      tma_load_3d(dst, &em.res, &rb[buf], tc.g * d.group_cols + col0, row0, tc.b);
+      if (mode && two) tma_load_3d(dst + 4096, &em.res_lo, &rb[buf], tc.g * d.group_cols + col0, row0, tc.b);
+    };
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(d, tile, mt, nt, BN);
+      const int acc = tcount & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16);
+      const int n_store = min(BN, ncols_out - tc.n0);
+      const int nspans = (n_store + SW - 1) / SW;
+      if (has_res && dbl && lane == 0 && par < nspans) {
+        bulk_wait_read<0>();
+        issue_res(tc, tc.n0 + par * SW, (int)(sc & 1));
+      }
+      mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int s = par; s < nspans; s += 2, ++sc) {
+        const int buf = dbl ? (int)(sc & 1) : 0;
+        const int col0 = tc.n0 + s * SW;
+        if (lane == 0) {
+          if (has_res && dbl) {
+            if (s + 2 < nspans) { bulk_wait_read<0>(); issue_res(tc, col0 + 2 * SW, buf ^ 1); }
+          } else if (has_res) {
+            bulk_wait_read<0>();
+            issue_res(tc, col0, 0);
+          } else if (dbl) {
+            bulk_wait_read<1>();   // the store issued two spans ago from this patch has finished reading shared memory
+          } else {
+            bulk_wait_read<0>();
+          }
+        }
+        __syncwarp();
+        if (has_res) {
+          const uint32_t u = buf ? use1 : use0;
+          mbar_wait(&rb[buf], u & 1);
+          if (buf) ++use1; else ++use0;
+        }
+        uint8_t* prow = pw + (dbl ? buf * 4096 : 0) + lane * 128;
+#pragma unroll 1
+        for (int g = 0; g < SW / 32; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + (uint32_t)(s * SW + g * 32), r);
+          const int gcol = tc.g * d.group_cols + col0 + g * 32;
+          const float* bp = d.bias ? d.bias + gcol : nullptr;
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          switch (pre_act) {
+            case 1: epi_math32<1>(v, bp, d.alpha); break;
+            case 2: epi_math32<2>(v, bp, d.alpha); break;
+            case 3: epi_math32<3>(v, bp, d.alpha); break;
+            default: epi_math32<0>(v, bp, d.alpha); break;
+          }
+          const int nrem = d.N - (col0 + g * 32);   // valid columns in this group (may be >= 32 or <= 0)
+          if (mode == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4* cell = reinterpret_cast<float4*>(prow + ((q ^ sw) << 4));
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (has_res) { const float4 rq = *cell; o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w; }
+              if (relu_after) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (4 * q + 3 >= nrem) {
+                if (4 * q >= nrem) o.x = 0.f;
+                if (4 * q + 1 >= nrem) o.y = 0.f;
+                if (4 * q + 2 >= nrem) o.z = 0.f;
+                if (4 * q + 3 >= nrem) o.w = 0.f;
+              }
+              *cell = o;
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {   // 4 x 16-byte chunks of 8 columns; chunk index within the 64-column row = 4g + h
+              uint4* chi = reinterpret_cast<uint4*>(prow + (((4 * g + h) ^ sw) << 4));
+              uint4* clo = reinterpret_cast<uint4*>(prow + 4096 + (((4 * g + h) ^ sw) << 4));
+              float e[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) e[c] = v[8 * h + c];
+              if (has_res) {
+                const uint4 rh = *chi;
+                float4 r0 = unpack4(make_uint2(rh.x, rh.y), fp16), r1 = unpack4(make_uint2(rh.z, rh.w), fp16);
+                if (two) {
+                  const uint4 rl = *clo;
+                  const float4 l0 = unpack4(make_uint2(rl.x, rl.y), fp16), l1 = unpack4(make_uint2(rl.z, rl.w), fp16);
+                  r0.x += l0.x; r0.y += l0.y; r0.z += l0.z; r0.w += l0.w;
+                  r1.x += l1.x; r1.y += l1.y; r1.z += l1.z; r1.w += l1.w;
+                }
+                e[0] += r0.x; e[1] += r0.y; e[2] += r0.z; e[3] += r0.w; e[4] += r1.x; e[5] += r1.y; e[6] += r1.z; e[7] += r1.w;
+              }
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float x0 = e[2 * c], x1 = e[2 * c + 1];
+                if (relu_after) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                if (8 * h + 2 * c >= nrem) x0 = 0.f;
+                if (8 * h + 2 * c + 1 >= nrem) x1 = 0.f;
+                bf16 h0, l0, h1, l1;
+                split_bf16(x0, h0, l0, fp16);
+                split_bf16(x1, h1, l1, fp16);
+                hw[c] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[c] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              *chi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (two) *clo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int row0 = tc.m0 + quad * 32;
+          const uint8_t* src = pw + (dbl ? buf * 4096 : 0);
+          tma_store_3d(&em.out, src, tc.g * d.group_cols + col0, row0, tc.b);
+          if (mode && two) tma_store_3d(&em.out_lo, src + 4096, tc.g * d.group_cols + col0, row0, tc.b);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (lane == 0) bulk_wait_all<0>();   // all stores complete before the CTA (and its shared memory) goes away
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -389,6 +686,27 @@ static EncodeTiledFn get_encode() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   });
   return fn;
+}
+
+static bool make_tmap_any(CUtensorMap* out, const void* base, int esize, int rank, const uint64_t* dims,
+                          const uint64_t* strides_elems, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { g_err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_elems[i] * (uint64_t)esize;
+      if (gstr[i - 1] % 16 != 0) { g_err = "tensor map stride not a multiple of 16 bytes"; return false; }
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) { g_err = "tensor map base not 16-byte aligned"; return false; }
+  CUresult r = enc(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return false; }
+  return true;
 }
 
 bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
@@ -424,6 +742,9 @@ struct GemmPlan {
   int rank5 = 0;
   int mt = 0, nt = 0, ntiles = 0;
   dim3 grid;
+  int tma_epi = 0;   // 1: gemm_tc_tma_kernel
+  int epi_mode = 0;  // 0 fp32 output, 1 16-bit plane output
+  EpiMaps em;
 };
 
 static int sm_count() {
@@ -447,6 +768,32 @@ static cudaError_t launch_bn(const GemmPlan* p, cudaStream_t st) {
   }
   gemm_tc_kernel<BN><<<p->grid, NUM_THREADS, TcCfg<BN>::SMEM, st>>>(p->maps, p->d, p->rank5, p->mt, p->nt, p->ntiles);
   return cudaGetLastError();
+}
+
+template <int BN>
+static cudaError_t launch_bn_tma(const GemmPlan* p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2<BN>::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_tc_tma_kernel<BN><<<p->grid, NUM_THREADS2, TcCfg2<BN>::SMEM, st>>>(p->maps, p->em, p->d, p->rank5, p->mt, p->nt, p->ntiles,
+                                                                            p->epi_mode);
+  return cudaGetLastError();
+}
+
+// The TMA epilogue handles: one group, no transposed output, exactly one of (fp32 | 16-bit plane) outputs, a residual of
+// the same kind as the output (or none).  Everything else takes the generic epilogue.
+static bool tma_epilogue_eligible(const GemmDesc& d) {
+  static const bool off = (getenv("DZ_GEMM_LEGACY_EPILOGUE") != nullptr);
+  if (off) return false;
+  if (d.groups != 1 || d.out_t != nullptr) return false;
+  const bool f = d.out_f32 != nullptr, h = d.out_bf != nullptr;
+  if (f == h) return false;
+  if (f && (d.res16 != nullptr || (d.ldo % 4) != 0 || (d.residual && (d.ldr % 4) != 0))) return false;
+  if (h && (d.residual != nullptr || (d.ldob % 8) != 0 || (d.res16 && (d.ldr16 % 8) != 0))) return false;
+  return true;
 }
 
 static int choose_bn(const GemmDesc& d) {
@@ -501,6 +848,38 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
   }
   p->mt = (d.M + BM - 1) / BM;
   p->nt = d.groups > 1 ? d.groups : (d.N + p->bn - 1) / p->bn;
+  if (tma_epilogue_eligible(d)) {
+    p->tma_epi = 1;
+    p->epi_mode = d.out_bf != nullptr ? 1 : 0;
+    bool ok = true;
+    if (p->epi_mode == 0) {
+      uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.batches};
+      uint64_t so[3] = {1, (uint64_t)d.ldo, (uint64_t)(d.batches > 1 ? d.of_bstride : (long long)d.ldo * d.M)};
+      uint32_t box[3] = {32, 32, 1};
+      ok = make_tmap_any(&p->em.out, d.out_f32, 4, 3, dims, so, box);
+      p->em.out_lo = p->em.out; p->em.res = p->em.out; p->em.res_lo = p->em.out;
+      if (ok && d.residual) {
+        uint64_t sr[3] = {1, (uint64_t)d.ldr, (uint64_t)(d.batches > 1 ? d.res_bstride : (long long)d.ldr * d.M)};
+        ok = make_tmap_any(&p->em.res, d.residual, 4, 3, dims, sr, box);
+      }
+    } else {
+      const int ncols = d.N > d.zero_pad_to ? d.N : d.zero_pad_to;
+      uint64_t dims[3] = {(uint64_t)ncols, (uint64_t)d.M, (uint64_t)d.batches};
+      uint64_t so[3] = {1, (uint64_t)d.ldob, (uint64_t)(d.batches > 1 ? d.ob_bstride : (long long)d.ldob * (d.M + d.out_row_off))};
+      uint32_t box[3] = {64, 32, 1};
+      const __nv_bfloat16* ob = (const __nv_bfloat16*)d.out_bf + (long long)d.out_row_off * d.ldob;
+      ok = make_tmap_any(&p->em.out, ob, 2, 3, dims, so, box);
+      p->em.out_lo = p->em.out; p->em.res = p->em.out; p->em.res_lo = p->em.out;
+      if (ok && d.out_planes > 1) ok = make_tmap_any(&p->em.out_lo, ob + d.ob_plane, 2, 3, dims, so, box);
+      if (ok && d.res16) {
+        uint64_t rdims[3] = {(uint64_t)d.N, (uint64_t)(d.M + d.res16_row_off), (uint64_t)d.batches};
+        uint64_t sr[3] = {1, (uint64_t)d.ldr16, (uint64_t)(d.batches > 1 ? d.res16_bstride : (long long)d.ldr16 * (d.M + d.res16_row_off))};
+        ok = make_tmap_any(&p->em.res, d.res16, 2, 3, rdims, sr, box);
+        if (ok && d.out_planes > 1) ok = make_tmap_any(&p->em.res_lo, (const __nv_bfloat16*)d.res16 + d.res16_plane, 2, 3, rdims, sr, box);
+      }
+    }
+    if (!ok) { delete p; return nullptr; }
+  }
   p->ntiles = p->mt * p->nt * d.batches;
   p->grid = dim3(p->ntiles < sm_count() ? p->ntiles : sm_count(), 1, 1);
   return p;
@@ -510,6 +889,14 @@ void gemm_plan_destroy(GemmPlan* p) { delete p; }
 const GemmDesc& gemm_plan_desc(const GemmPlan* p) { return p->d; }
 
 cudaError_t gemm_plan_launch(const GemmPlan* p, cudaStream_t st) {
+  if (p->tma_epi) {
+    switch (p->bn) {
+      case 64: return launch_bn_tma<64>(p, st);
+      case 128: return launch_bn_tma<128>(p, st);
+      case 256: return launch_bn_tma<256>(p, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (p->bn) {
     case 64: return launch_bn<64>(p, st);
     case 128: return launch_bn<128>(p, st);

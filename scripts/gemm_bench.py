@@ -14,7 +14,7 @@ def bench(M, N, K, variant, bn=0, iters=20):
     A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) / K ** 0.5
     Ap, Wp = to_planes(A), to_planes(W)
     ldn = rup(N, 8)
-    bias = torch.randn(rup(N, 32) + 32, device=dev)
+    bias = torch.randn(rup(N, 64) + 64, device=dev)
     res = torch.randn(M, ldn, device=dev)
     of = torch.empty(M, ldn, device=dev); ob = torch.empty(2, M, ldn, device=dev, dtype=torch.bfloat16)
     d = _lib.GemmDesc.default()

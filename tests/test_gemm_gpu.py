@@ -29,7 +29,7 @@ def test_linear_epilogue(impl, npass, M, N, K, bn):
     dev = "cuda"
     A = torch.randn(M, K, device=dev)
     W = torch.randn(N, K, device=dev) / K ** 0.5
-    bias = torch.randn(rup(N, 32) + 32, device=dev)
+    bias = torch.randn(rup(N, 64) + 64, device=dev)
     res = torch.randn(M, rup(N, 8), device=dev)
     Ap, Wp = to_planes(A), to_planes(W)
     ldn = rup(N, 8)
@@ -156,7 +156,7 @@ def test_conv2d_as_gemm(impl, npass, B, H, W, Cin, Cout, ks, stride, res):
     dev = "cuda"
     x = torch.randn(B, Cin, H, W, device=dev)
     w = torch.randn(Cout, Cin, ks, ks, device=dev) / (Cin * ks * ks) ** 0.5
-    bias = torch.randn(Cout + 64, device=dev)
+    bias = torch.randn(rup(Cout, 64) + 64, device=dev)
     pad = 1 if ks == 3 else 0
     Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
     Wp, Wop = W + 2, Wo + 2
