@@ -159,8 +159,13 @@ class AgglomerativeClustering:
         emb = embeddings.copy()
         with np.errstate(divide="ignore", invalid="ignore"):
             emb /= np.linalg.norm(emb, axis=-1, keepdims=True)
+        import os as _os, time as _time
+        _t0 = _time.perf_counter()
         Z = device_linkage_centroid(emb, self.device)
+        _t1 = _time.perf_counter()
         clusters = fcluster_distance(Z, self.threshold) - 1
+        if _os.environ.get("DZ_TIMING") is not None:
+            print(f"[dz timing] linkage N={n}: device pdist+linkage {(_t1 - _t0) * 1e3:.1f} ms, fcluster {(_time.perf_counter() - _t1) * 1e3:.1f} ms")
         uniq, counts = np.unique(clusters, return_counts=True)
         large = uniq[counts >= mcs]
         nlarge = len(large)

@@ -246,116 +246,142 @@ cudaError_t launch_conv0(const Conv0Args& a, int B, bool large, cudaStream_t st)
 // ------------------------------------------------------------------------------------------------
 template <int NV>  // float4 chunks per lane: C <= 128 * NV
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(LnArgs a) {
+  // gamma / beta / prescale staged once per CTA; each warp then walks rows with a grid stride
+  extern __shared__ float lnsm[];
+  float* sg = lnsm;
+  float* sb = sg + NV * 128;
+  float* sp = sb + NV * 128;
+  for (int i = threadIdx.x; i < NV * 128; i += blockDim.x) {
+    sg[i] = i < a.C ? a.gamma[i] : 0.f;
+    sb[i] = i < a.C ? a.beta[i] : 0.f;
+    sp[i] = (a.prescale != nullptr && i < a.C) ? a.prescale[i] : 1.f;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= a.rows) return;
-  const float* xr = a.x + row * a.ldx;
-  float v[NV * 4];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c + 3 < a.C) {
-      t = *reinterpret_cast<const float4*>(xr + c);
-    } else {
-      if (c < a.C) t.x = xr[c];
-      if (c + 1 < a.C) t.y = xr[c + 1];
-      if (c + 2 < a.C) t.z = xr[c + 2];
-    }
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-  if (a.mix != nullptr && a.mix_src == 1) {
-    float* mr = a.mix + row * a.ldx;
+  const bool vec = (a.C % 4) == 0;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < a.rows; row += (long long)gridDim.x * 8) {
+    const float* xr = a.x + row * a.ldx;
+    float v[NV * 4];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c + j < a.C) mr[c + j] = (a.mix_init ? 0.f : mr[c + j]) + a.mix_w * v[4 * i + j];
-    }
-  }
-  if (a.prescale != nullptr) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c + j < a.C) v[4 * i + j] *= __ldg(a.prescale + c + j);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NV * 4; ++i) s += v[i];
-  const float mean = warp_sum(s) / a.C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (c + j < a.C) { const float dl = v[4 * i + j] - mean; q += dl * dl; }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / a.C + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float y = 0.f;
-      if (c + j < a.C) y = apply_act((v[4 * i + j] - mean) * rstd * __ldg(a.gamma + c + j) + __ldg(a.beta + c + j), a.act);
-      v[4 * i + j] = y;
-    }
-  }
-  if (a.mix != nullptr && a.mix_src == 2) {
-    float* mr = a.mix + row * a.ldx;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c + j < a.C) mr[c + j] = (a.mix_init ? 0.f : mr[c + j]) + a.mix_w * v[4 * i + j];
-    }
-  }
-  if (a.y_f32 != nullptr) {
-    float* yr = a.y_f32 + row * a.ldy;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c + 3 < a.C) {
-        *reinterpret_cast<float4*>(yr + c) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        t = *reinterpret_cast<const float4*>(xr + c);
       } else {
+        if (c < a.C) t.x = xr[c];
+        if (c + 1 < a.C) t.y = xr[c + 1];
+        if (c + 2 < a.C) t.z = xr[c + 2];
+      }
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    if (a.mix != nullptr && a.mix_src == 1) {
+      float* mr = a.mix + row * a.ldx;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + j < a.C) yr[c + j] = v[4 * i + j];
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (vec && c + 3 < a.C) {
+          float4 m = a.mix_init ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(mr + c);
+          m.x += a.mix_w * v[4 * i]; m.y += a.mix_w * v[4 * i + 1]; m.z += a.mix_w * v[4 * i + 2]; m.w += a.mix_w * v[4 * i + 3];
+          *reinterpret_cast<float4*>(mr + c) = m;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < a.C) mr[c + j] = (a.mix_init ? 0.f : mr[c + j]) + a.mix_w * v[4 * i + j];
+        }
       }
     }
-  }
-  if (a.y_bf != nullptr) {
-    bf16* hr = a.y_bf + row * a.ldb;
+    if (a.prescale != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 p4 = *reinterpret_cast<const float4*>(sp + (lane + 32 * i) * 4);
+        v[4 * i] *= p4.x; v[4 * i + 1] *= p4.y; v[4 * i + 2] *= p4.z; v[4 * i + 3] *= p4.w;
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) s += v[i];   // cells beyond C hold exact zeros
+    const float mean = warp_sum(s) / a.C;
+    float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
-      if (c + 3 < a.ldb) {  // ldb % 8 == 0: whole chunk inside the (zero padded) row
-        bf16 h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(v[4 * i + j], h[j], l[j], a.fp16);
-        uint2 hw, lw;
-        hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-        hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-        lw.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-        lw.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-        *reinterpret_cast<uint2*>(hr + c) = hw;
-        if (a.planes > 1) *reinterpret_cast<uint2*>(hr + a.bf_plane + c) = lw;
+      for (int j = 0; j < 4; ++j)
+        if (c + j < a.C) { const float dl = v[4 * i + j] - mean; q += dl * dl; }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / a.C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 g4 = *reinterpret_cast<const float4*>(sg + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = 0.f;
+        if (c + j < a.C) y = apply_act((v[4 * i + j] - mean) * rstd * gg[j] + bb[j], a.act);
+        v[4 * i + j] = y;
+      }
+    }
+    if (a.mix != nullptr && a.mix_src == 2) {
+      float* mr = a.mix + row * a.ldx;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (vec && c + 3 < a.C) {
+          float4 m = a.mix_init ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(mr + c);
+          m.x += a.mix_w * v[4 * i]; m.y += a.mix_w * v[4 * i + 1]; m.z += a.mix_w * v[4 * i + 2]; m.w += a.mix_w * v[4 * i + 3];
+          *reinterpret_cast<float4*>(mr + c) = m;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < a.C) mr[c + j] = (a.mix_init ? 0.f : mr[c + j]) + a.mix_w * v[4 * i + j];
+        }
+      }
+    }
+    if (a.y_f32 != nullptr) {
+      float* yr = a.y_f32 + row * a.ldy;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c + 3 < a.C) {
+          *reinterpret_cast<float4*>(yr + c) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < a.C) yr[c + j] = v[4 * i + j];
+        }
+      }
+    }
+    if (a.y_bf != nullptr) {
+      bf16* hr = a.y_bf + row * a.ldb;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c + 3 < a.ldb) {  // ldb % 8 == 0: whole chunk inside the (zero padded) row
+          bf16 h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_bf16(v[4 * i + j], h[j], l[j], a.fp16);
+          uint2 hw, lw;
+          hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+          hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+          lw.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+          lw.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+          *reinterpret_cast<uint2*>(hr + c) = hw;
+          if (a.planes > 1) *reinterpret_cast<uint2*>(hr + a.bf_plane + c) = lw;
+        }
       }
     }
   }
 }
 
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a.rows + 7) / 8);
-  if (a.C <= 256) layernorm_rows_kernel<2><<<grid, 256, 0, st>>>(a);
-  else if (a.C <= 512) layernorm_rows_kernel<4><<<grid, 256, 0, st>>>(a);
-  else if (a.C <= 1024) layernorm_rows_kernel<8><<<grid, 256, 0, st>>>(a);
+  const long long want = (a.rows + 7) / 8;
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  if (a.C <= 256) layernorm_rows_kernel<2><<<grid, 256, 3 * 2 * 128 * sizeof(float), st>>>(a);
+  else if (a.C <= 512) layernorm_rows_kernel<4><<<grid, 256, 3 * 4 * 128 * sizeof(float), st>>>(a);
+  else if (a.C <= 1024) layernorm_rows_kernel<8><<<grid, 256, 3 * 8 * 128 * sizeof(float), st>>>(a);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -189,6 +189,19 @@ class DiariZenPipeline:
         dev = self.device
         L = self._L
         Nw = wav.shape[0]
+        import time as _time
+        timing = {}
+        _tm = os.environ.get("DZ_TIMING") is not None
+
+        def _mark(name, _t=[None]):
+            if not _tm:
+                return
+            torch.cuda.synchronize()
+            now = _time.perf_counter()
+            if _t[0] is not None:
+                timing[name] = timing.get(name, 0.0) + (now - _t[0])
+            _t[0] = now
+        _mark("start")
         window, step, Cn = self._windows(Nw)
         chunk_step_s = self.segmentation_step * self.seg_duration
         T = self._segmentation.num_frames(window)
@@ -205,6 +218,7 @@ class DiariZenPipeline:
             b = min(a + bs, c1)
             self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg_local[a - c0:b - c0])
         seg = gather_windows(seg_local, Cn, world).contiguous()
+        _mark("segmentation")
         st = vp(torch.cuda.current_stream().cuda_stream)
         if self.apply_median_filtering:
             filt = torch.empty_like(seg)
@@ -225,6 +239,7 @@ class DiariZenPipeline:
         # embeddings (chunk crops as the reference computes them: io.py:359-364)
         e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(Cn)]
         same = all(e_starts[c] == c * step for c in range(Cn))
+        _mark("count_masks")
         emb_local = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
         ebs = max(1, self.embedding_batch_size // S)
         for a in range(c0, c1, ebs):
@@ -235,6 +250,7 @@ class DiariZenPipeline:
                 wv = torch.stack([wdev[e_starts[c]:e_starts[c] + window] for c in range(a, b)])
             emb_local[a - c0:b - c0] = self._embedding.embed_windows(wv, masks[a:b])
         emb = gather_windows(emb_local, Cn, world)          # the single data-path collective (NCCL all-gather)
+        _mark("embedding")
         if rank != 0:
             return {}
         emb_np = emb.cpu().numpy()
@@ -242,6 +258,7 @@ class DiariZenPipeline:
         hard, _, centroids = self.clustering(embeddings=emb_np, segmentations=None, min_clusters=self.min_speakers,
                                              max_clusters=self.max_speakers,
                                              frame_stats=(stats_np[..., 0], stats_np[..., 1], T))
+        _mark("clustering")
         hard = np.array(hard, dtype=np.int8, copy=True)
         hard[stats_np[..., 0] == 0] = -2                                   # inactive speakers (inference.py:166-170)
         K = int(hard.max()) + 1 if hard.size and hard.max() >= 0 else 1
@@ -253,8 +270,9 @@ class DiariZenPipeline:
         _lib.check(L.dz_reconstruct(vp(seg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(count.data_ptr()), Cn, T, S,
                                     Kk, Kout, F, vp(disc.data_ptr()), None, st))
         discrete = disc.cpu().numpy()
+        _mark("reconstruct")
         out = {"segmentations": seg, "count": count, "embeddings": emb_np, "hard_clusters": hard, "discrete": discrete,
-               "centroids": centroids, "num_chunks": Cn, "num_frames": T}
+               "centroids": centroids, "num_chunks": Cn, "num_frames": T, "timing": timing}
         self.last = out
         return out
 
