@@ -214,9 +214,19 @@ class DiariZenPipeline:
         c0, c1, per = window_range(Cn, rank, world)
         seg_local = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
         bs = self.segmentation_batch_size
+        # The engines plan (workspace + tensor maps) per batch shape: the ragged last batch is padded to the full
+        # batch size instead of triggering a re-plan (two multi-GB reallocations per recording otherwise).
+        seg_tail = None
         for a in range(c0, c1, bs):
             b = min(a + bs, c1)
-            self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg_local[a - c0:b - c0])
+            if b - a == bs or (c1 - c0) < bs:
+                self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg_local[a - c0:b - c0])
+            else:
+                wpad = torch.zeros((bs, window), device=dev, dtype=torch.float32)
+                wpad[:b - a] = chunks[a:b]
+                seg_tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
+                self._segmentation.hard(wpad, want_logp=False, ml_out=seg_tail)
+                seg_local[a - c0:b - c0] = seg_tail[:b - a]
         seg = gather_windows(seg_local, Cn, world).contiguous()
         _mark("segmentation")
         st = vp(torch.cuda.current_stream().cuda_stream)
@@ -248,7 +258,11 @@ class DiariZenPipeline:
                 wv = chunks[a:b].contiguous()
             else:
                 wv = torch.stack([wdev[e_starts[c]:e_starts[c] + window] for c in range(a, b)])
-            emb_local[a - c0:b - c0] = self._embedding.embed_windows(wv, masks[a:b])
+            mk = masks[a:b]
+            if b - a < ebs and (c1 - c0) >= ebs:   # pad the ragged last batch (see above)
+                wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
+                mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
+            emb_local[a - c0:b - c0] = self._embedding.embed_windows(wv, mk)[:b - a]
         emb = gather_windows(emb_local, Cn, world)          # the single data-path collective (NCCL all-gather)
         _mark("embedding")
         if rank != 0:
