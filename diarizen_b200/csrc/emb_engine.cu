@@ -221,24 +221,21 @@ static int emb_plan(dz_emb* s, int B, int N, int S, int T) {
     c.out = act[0].p; c.out_plane = act[0].plane; c.planes = P; c.fp16 = FP;
     conv1_args = c;
   }
-  // Zero borders: a buffer may be written with a geometry (H, W, C) only if every cell outside that geometry's
-  // interior is zero.  Whenever a buffer is about to be written with a geometry different from the one it last held
-  // (stage transitions, and the first use in every forward since the previous forward left other geometries behind)
-  // it is cleared first; the clears are part of the static launch list.
+  // Zero borders: a buffer is read by the next convolution with geometry (H, W, C); its border columns w = 0 and
+  // w = W + 1 must be zero (the interior is fully overwritten by the producer, rows outside [0, H) are never addressed:
+  // TMA zero-fills them).  Whenever a buffer is about to be written with a geometry different from the one it last held
+  // (stage transitions, and the first use in every forward) only those two columns are cleared.
   long long geom[4] = {-1, -1, -1, -1};
   auto ensure_geom = [&](int bi, int Hh, int Ww, int Cc, const std::string& nm) {
     const long long g = ((long long)Hh << 40) | ((long long)Ww << 16) | Cc;
     if (geom[bi] == g) return;
     geom[bi] = g;
     bf16* p = act[bi].p;
-    const size_t elems = (size_t)B * Hh * (Ww + 2) * Cc + 256;
-    const size_t plane = (size_t)act[bi].plane;
+    const long long plane = act[bi].plane;
+    const long long rows = (long long)B * Hh;
     const int np = P;
-    s->steps.push_back({nm, [p, elems, plane, np](cudaStream_t st) {
-      cudaError_t e = cudaMemsetAsync(p, 0, elems * 2, st);
-      if (e == cudaSuccess && np > 1) e = cudaMemsetAsync(p + plane, 0, elems * 2, st);
-      return e;
-    }, 0.0, (double)elems * 2 * np});
+    s->steps.push_back({nm, [=](cudaStream_t st) { return launch_zero_borders(p, plane, np, rows, Ww, Cc, st); }, 0.0,
+                        (double)rows * 2 * Cc * 2 * np});
   };
   auto conv = [&](const std::string& nm, Planes in, int Hin, int Win, int Cin, const Weight& W, int ks, int stride, Planes out,
                   const Planes* res, int act) {

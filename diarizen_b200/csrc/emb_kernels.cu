@@ -186,6 +186,26 @@ cudaError_t launch_emb_conv1(const Conv1Args& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// zero the two border columns (w = 0 and w = W + 1) of a zero-bordered NHWC plane set [B*H][W + 2][C] (+ slack)
+__global__ void zero_borders_kernel(bf16* __restrict__ p, long long plane, int planes, long long rows, int W, int C) {
+  const long long total = rows * 2 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const long long row = r >> 1;
+    const int side = (int)(r & 1);
+    const long long o = (row * (W + 2) + (side ? W + 1 : 0)) * C + c;
+    p[o] = __float2bfloat16_rn(0.f);
+    if (planes > 1) p[plane + o] = __float2bfloat16_rn(0.f);
+  }
+}
+cudaError_t launch_zero_borders(bf16* p, long long plane, int planes, long long rows, int W, int C, cudaStream_t st) {
+  const long long total = rows * 2 * C;
+  const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  zero_borders_kernel<<<grid, 256, 0, st>>>(p, plane, planes, rows, W, C);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K15 masked statistics pooling.  x: zero-bordered NHWC planes [b][h][1 + w][C] (C = 256, h < H = 10);
 // masks [b][S][T] -> weights nearest-interpolated to W frames through widx[w];

@@ -32,5 +32,6 @@ cudaError_t launch_fbank(const FbankArgs& a, int B, cudaStream_t st);
 cudaError_t launch_fbank_mean(const float* fb, int B, int F, float* mean, cudaStream_t st);
 cudaError_t launch_emb_conv1(const Conv1Args& a, cudaStream_t st);
 cudaError_t launch_stats_pool(const PoolArgs& a, int B, cudaStream_t st);
+cudaError_t launch_zero_borders(__nv_bfloat16* p, long long plane, int planes, long long rows, int W, int C, cudaStream_t st);
 
 }  // namespace dz

@@ -385,8 +385,12 @@ static constexpr int PATCH2_BYTES = 8192;                // per epilogue warp: 2
 template <int BN>
 struct TcCfg2 {
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
-  static constexpr int NSTAGE = (BN == 256) ? 3 : (BN == 128 ? 4 : 5);
-  static constexpr int SMEM = NSTAGE * STAGE_BYTES + NUM_EPI2 * PATCH2_BYTES + 1024 + 256;
+  // BN = 64 (narrow outputs: ResNet layer 1/2, conv stack): 4 stages so that two CTAs fit per SM - with so little work
+  // per tile, tiles in flight matter more than ring depth.
+  static constexpr int NSTAGE = (BN == 128) ? 4 : 3;
+  static constexpr int PATCH = (BN == 64) ? 4096 : PATCH2_BYTES;   // BN = 64: single 4 KB patch per warp (2 CTAs per SM)
+  static constexpr int SMEM = NSTAGE * STAGE_BYTES + NUM_EPI2 * PATCH + 1024 + 256;
+  static constexpr int MIN_CTAS = (BN == 64) ? 2 : 1;
 };
 
 DZ_DEVINL float4 unpack4(uint2 w, int fp16) {
@@ -419,14 +423,14 @@ DZ_DEVINL void epi_math32(float (&v)[32], const float* __restrict__ bias, float 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS2, 1)
+__global__ void __launch_bounds__(NUM_THREADS2, (BN == 64) ? 2 : 1)
 gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiMaps em, const GemmDesc d, const int a_rank5,
                    const int mt, const int nt, const int ntiles, const int mode) {
   using C = TcCfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* patches = smem + C::NSTAGE * C::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(patches + NUM_EPI2 * PATCH2_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(patches + NUM_EPI2 * C::PATCH);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
   uint64_t* tmem_full = empty_bar + C::NSTAGE;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
@@ -517,12 +521,13 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
     const int ew = warp - 2;          // 0..7
     const int quad = warp & 3;        // TMEM lane quarter
     const int par = ew >> 2;          // span parity served by this warp
-    uint8_t* pw = patches + ew * PATCH2_BYTES;
+    uint8_t* pw = patches + ew * C::PATCH;
     uint64_t* rb = res_bar + ew * 2;
     const int SW = mode ? 64 : 32;
     const bool two = d.out_planes > 1;
     const bool has_res = mode ? (d.res16 != nullptr) : (d.residual != nullptr);
-    const bool dbl = !(mode && two);  // double-buffered patches unless both planes are needed (hi | lo share the 8 KB)
+    // double-buffered patches unless both planes are needed (hi | lo share the 8 KB) or the patch is the 4 KB one
+    const bool dbl = (BN != 64) && !(mode && two);
     const int fp16 = d.fp16;
     const int sw = lane & 7;
     const bool relu_after = d.act_after_res && d.act == 3;
@@ -810,6 +815,11 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
   GemmPlan* p = new GemmPlan();
   p->d = d;
   p->bn = force_bn ? force_bn : choose_bn(d);
+  bool want_tma = tma_epilogue_eligible(d);
+  if (want_tma && p->bn == 64 && d.out_bf != nullptr && d.out_planes > 1) {
+    // the 4 KB patch of the BN = 64 TMA configuration cannot hold hi + lo planes
+    if (force_bn == 0) p->bn = 128; else want_tma = false;
+  }
   if (d.groups > 1 && d.N > p->bn) { g_err = "grouped GEMM needs N <= BN"; delete p; return nullptr; }
   if (d.npass != 1 && d.npass != 3) { g_err = "npass must be 1 or 3"; delete p; return nullptr; }
   p->rank5 = (d.conv_runs == 0 && d.a_kinner != d.K) ? 1 : 0;
@@ -848,8 +858,9 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
   }
   p->mt = (d.M + BM - 1) / BM;
   p->nt = d.groups > 1 ? d.groups : (d.N + p->bn - 1) / p->bn;
-  if (tma_epilogue_eligible(d)) {
+  if (want_tma) {
     p->tma_epi = 1;
+
     p->epi_mode = d.out_bf != nullptr ? 1 : 0;
     bool ok = true;
     if (p->epi_mode == 0) {
@@ -881,7 +892,10 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
     if (!ok) { delete p; return nullptr; }
   }
   p->ntiles = p->mt * p->nt * d.batches;
-  p->grid = dim3(p->ntiles < sm_count() ? p->ntiles : sm_count(), 1, 1);
+  {
+    const int ctas = sm_count() * ((p->tma_epi && p->bn == 64) ? 2 : 1);
+    p->grid = dim3(p->ntiles < ctas ? p->ntiles : ctas, 1, 1);
+  }
   return p;
 }
 
