@@ -351,11 +351,11 @@ def run_pipeline_bench(args, world, rank, local, dist):
     peaks = measured_peaks()
     # per-class device time of one batch of each network (CUDA events per launch), scaled by the number of batches
     window = int(dur * SR)
-    bsz = args.batch
+    bsz = pipe.engine_windows
     wb = wav_dev[: window].repeat(bsz, 1).contiguous()
     seg_prof = pipe._segmentation.profile(wb)
     seg_prof = pipe._segmentation.profile(wb)
-    ebs = max(1, bsz // 4)
+    ebs = pipe.engine_emb_windows
     pipe._embedding.embed_windows(wb[:ebs], torch.ones(ebs, 4, T, device="cuda"))
     emb_prof = pipe._embedding.profile()
     n_seg_b, n_emb_b = Cn / bsz / world, Cn / ebs / world
@@ -404,7 +404,8 @@ def run_pipeline_bench(args, world, rank, local, dist):
         "data": "synthetic",
         "config": {"workload": f"{args.arch} full pipeline (segmentation + ResNet34 embeddings + centroid AHC + reconstruction), "
                                f"{args.minutes:g} min synthetic 16 kHz meeting per GPU, {dur:g} s windows / {dur * 0.1:g} s step (BASELINE.json configs[2])",
-                   "arch": args.arch, "window_s": dur, "windows_per_recording": Cn, "batch": bsz,
+                   "arch": args.arch, "window_s": dur, "windows_per_recording": Cn, "config_batch_size": args.batch,
+                   "engine_windows_per_call": {"segmentation": bsz, "embedding": ebs},
                    "recordings_per_step": n_rec,
                    "parallelism": f"each recording window-sharded over {world} rank(s), one NCCL all-gather of segmentations + embeddings, clustering on rank 0",
                    "clusters_found": int(last["hard_clusters"].max()) + 1,
