@@ -245,7 +245,7 @@ cudaError_t launch_conv0(const Conv0Args& a, int B, bool large, cudaStream_t st)
 // reference: components.py:63-70, :305, :923-941, :983; conformer.py ln_norm; model_wavlm_conformer.py:235-236,253-257.
 // ------------------------------------------------------------------------------------------------
 template <int NV>  // float4 chunks per lane: C <= 128 * NV
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(LnArgs a) {
+__global__ void __launch_bounds__(256, 3) layernorm_rows_kernel(LnArgs a) {
   // gamma / beta / prescale staged once per CTA; each warp then walks rows with a grid stride
   extern __shared__ float lnsm[];
   float* sg = lnsm;
