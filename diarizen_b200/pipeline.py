@@ -185,9 +185,16 @@ class DiariZenPipeline:
         has_last = (num_samples < window) or ((num_samples - window) % step > 0)
         return window, step, n_full + int(has_last)
 
-    def diarize_waveform(self, wav: torch.Tensor) -> Dict[str, Any]:
-        """wav (N,) fp32 -> dict with every intermediate the parity tests compare (rank 0 only under torch.distributed)."""
+    def diarize_waveform(self, wav: torch.Tensor, shard: Optional[bool] = None) -> Dict[str, Any]:
+        """wav (N,) fp32 -> dict with every intermediate the parity tests compare.
+
+        shard: window-shard this recording over the ranks of the initialised torch.distributed group (one all-gather,
+        result on rank 0 only).  Default: shard when a process group exists.  Policy for many recordings:
+        give whole recordings to ranks (`shard=False`, no collective) and window-shard only when there are fewer
+        recordings than ranks."""
         dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        if shard is False:
+            dist = None
         rank = dist.get_rank() if dist else 0
         world = dist.get_world_size() if dist else 1
         dev = self.device
@@ -316,10 +323,10 @@ class DiariZenPipeline:
                 ann[Segment(mid(a), mid(b)), k] = k
         return ann
 
-    def __call__(self, in_wav, sess_name=None):
+    def __call__(self, in_wav, sess_name=None, shard: Optional[bool] = None):
         wav = load_waveform(in_wav)
         print("Extracting segmentations.")
-        res = self.diarize_waveform(wav)
+        res = self.diarize_waveform(wav, shard=shard)
         if not res:
             return None
         result = self.to_annotation(res["discrete"], sess_name)
