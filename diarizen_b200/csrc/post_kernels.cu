@@ -307,7 +307,9 @@ __global__ void assign_kernel(const double* __restrict__ soft, int C, int S, int
     unsigned used = 0;
     bool ok = true;
     double v = 0.0;
-    for (int s = 0; s < S; ++s) {
+    // speaker 0 is the most significant digit: among equal totals the lexicographically smallest map wins, which is what
+    // scipy's solver returns for the all-equal (NaN-filled) rows of inactive speakers
+    for (int s = S - 1; s >= 0; --s) {
       const int k = t % base - 1;
       t /= base;
       a[s] = k;
@@ -389,4 +391,103 @@ int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, voi
   return DZ_OK;
 }
 
+}  // extern "C"
+
+// ================================================================================================
+// VBx (variational Bayes GMM over PLDA-space x-vectors): the two halves of one iteration, float64.
+// reference: diarizen/clustering/VBx.py:86-111 (loopProb = 0 branch; the HMM branch is unreachable there).
+//   model update  : Ns = sum_t gamma[t,s]; invL[s,d] = 1 / (1 + Fa/Fb * Ns * Phi[d]); alpha[s,d] = Fa/Fb * invL[s,d] * sum_t gamma[t,s] rho[t,d]
+//   responsibility: log_p[t,s] = Fa * (rho[t].alpha[s] - 0.5 * sum_d (invL[s,d] + alpha[s,d]^2) Phi[d] + G[t]);
+//                   gamma[t,s] = exp(log_p + log(pi_s + 1e-8) - logsumexp_s(...)); pi_new[s] = sum_t gamma[t,s]; logpX = sum_t logsumexp
+// ================================================================================================
+namespace dz {
+
+__global__ void __launch_bounds__(256) vbx_model_kernel(const double* __restrict__ gamma, const double* __restrict__ rho,
+                                                        const double* __restrict__ Phi, int N, int D, int S, double fafb,
+                                                        double* __restrict__ alpha, double* __restrict__ invL) {
+  __shared__ double sc[32];
+  const int s = blockIdx.x;
+  double ns = 0.0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) ns += gamma[(long long)t * S + s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = ns;
+  __syncthreads();
+  ns = 0.0;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) ns += sc[w];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double acc = 0.0;
+    for (int t = 0; t < N; ++t) acc += gamma[(long long)t * S + s] * rho[(long long)t * D + d];
+    const double il = 1.0 / (1.0 + fafb * ns * Phi[d]);
+    invL[s * D + d] = il;
+    alpha[s * D + d] = fafb * il * acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) vbx_resp_kernel(const double* __restrict__ rho, const double* __restrict__ G,
+                                                       const double* __restrict__ alpha, const double* __restrict__ invL,
+                                                       const double* __restrict__ Phi, const double* __restrict__ pi, int N, int D,
+                                                       int S, double Fa, double* __restrict__ gamma, double* __restrict__ pi_acc,
+                                                       double* __restrict__ logpx_acc) {
+  extern __shared__ double sh[];   // [S] constant term per speaker, [S] log prior
+  double* cst = sh;
+  double* lpi = sh + S;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    double c = 0.0;
+    for (int d = 0; d < D; ++d) c += (invL[s * D + d] + alpha[s * D + d] * alpha[s * D + d]) * Phi[d];
+    cst[s] = 0.5 * c;
+    lpi[s] = log(pi[s] + 1e-8);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * 8 + warp; t < N; t += gridDim.x * 8) {
+    const double* r = rho + (long long)t * D;
+    double mx = -INFINITY;
+    // pass 1: scores (kept in gamma as scratch), running max
+    for (int s = 0; s < S; ++s) {
+      double dot = 0.0;
+      for (int d = lane; d < D; d += 32) dot += r[d] * alpha[s * D + d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const double v = Fa * (dot - cst[s] + G[t]) + lpi[s];
+      if (lane == 0) gamma[(long long)t * S + s] = v;
+      mx = fmax(mx, v);
+    }
+    __syncwarp();
+    double se = 0.0;
+    for (int s = lane; s < S; s += 32) se += exp(gamma[(long long)t * S + s] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const double lse = mx + log(se);
+    for (int s = lane; s < S; s += 32) {
+      const double g = exp(gamma[(long long)t * S + s] - lse);
+      gamma[(long long)t * S + s] = g;
+      atomicAdd(&pi_acc[s], g);
+    }
+    if (lane == 0) atomicAdd(logpx_acc, lse);
+  }
+}
+
+}  // namespace dz
+
+extern "C" {
+int dz_vbx_model(const double* gamma_dev, const double* rho_dev, const double* phi_dev, int N, int D, int S, double fa_over_fb,
+                 double* alpha_dev, double* invl_dev, void* stream) {
+  if (!gamma_dev || !rho_dev || !phi_dev || !alpha_dev || !invl_dev || N < 1 || D < 1 || S < 1) return fail(DZ_ERR_INVALID, "bad argument");
+  dz::vbx_model_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(gamma_dev, rho_dev, phi_dev, N, D, S, fa_over_fb, alpha_dev, invl_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
+/* pi_acc_dev [S] and logpx_acc_dev [1] must be zeroed by the caller; gamma_dev [N][S] is overwritten */
+int dz_vbx_resp(const double* rho_dev, const double* g_dev, const double* alpha_dev, const double* invl_dev, const double* phi_dev,
+                const double* pi_dev, int N, int D, int S, double Fa, double* gamma_dev, double* pi_acc_dev, double* logpx_acc_dev,
+                void* stream) {
+  if (!rho_dev || !g_dev || !alpha_dev || !invl_dev || !phi_dev || !pi_dev || !gamma_dev || !pi_acc_dev || !logpx_acc_dev)
+    return fail(DZ_ERR_INVALID, "bad argument");
+  const int grid = (N + 7) / 8 < 148 * 4 ? (N + 7) / 8 : 148 * 4;
+  dz::vbx_resp_kernel<<<grid, 256, sizeof(double) * 2 * S, (cudaStream_t)stream>>>(rho_dev, g_dev, alpha_dev, invl_dev, phi_dev, pi_dev,
+                                                                                  N, D, S, Fa, gamma_dev, pi_acc_dev, logpx_acc_dev);
+  CK_LAUNCH();
+  return DZ_OK;
+}
 }  // extern "C"

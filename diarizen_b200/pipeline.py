@@ -28,7 +28,7 @@ import torch
 from . import _lib
 from .annotation import Annotation, Segment
 from .archs import SegArch, arch_from_reference_config, get_arch, init_state_dict
-from .clustering import AgglomerativeClustering
+from .clustering import AgglomerativeClustering, VBxClustering
 from .embedding import EmbeddingModel
 from .segmentation import SegmentationModel
 from .sharding import gather_windows, window_range
@@ -112,8 +112,15 @@ class DiariZenPipeline:
             self.clustering.min_cluster_size = clu["min_cluster_size"]
             self.clustering.threshold = clu["ahc_threshold"]
         elif clu["method"] == "VBxClustering":
-            raise NotImplementedError("VBxClustering (PLDA + VB-GMM refinement) is not implemented yet in diarizen_b200; "
-                                      "use clustering.method = 'AgglomerativeClustering' (the recipes' setting)")
+            # inference.py:72-83
+            self.clustering = VBxClustering(metric="cosine", device=self.device)
+            self.clustering.ahc_criterion = clu["ahc_criterion"]
+            self.clustering.ahc_threshold = clu["ahc_threshold"]
+            self.clustering.Fa = clu["Fa"]
+            self.clustering.Fb = clu["Fb"]
+            self.clustering.plda_dir = str(clu["plda_dir"]) if "plda_dir" in clu else str(Path(diarizen_hub) / "plda")
+            self.clustering.lda_dim = clu["lda_dim"]
+            self.clustering.maxIters = clu["max_iters"]
         else:
             raise ValueError(f"Unsupported clustering method: {clu['method']}")
         if _seg is None:
@@ -161,7 +168,8 @@ class DiariZenPipeline:
                          segmentation_step: float = 0.1, batch_size: int = 32, min_cluster_size: int = 30,
                          ahc_threshold: float = 0.70, min_speakers: int = 1, max_speakers: int = 20,
                          apply_median_filtering: bool = True, classifier_gain: float = 1.0, precision: str = "fp16",
-                         rttm_out_dir: Optional[str] = None, device=None, emb_state_dict=None) -> "DiariZenPipeline":
+                         rttm_out_dir: Optional[str] = None, device=None, emb_state_dict=None,
+                         vbx: Optional[dict] = None) -> "DiariZenPipeline":
         """Seeded random weights of the named architecture (no checkpoint is reachable offline: SURVEY.md 0.8)."""
         from .archs import init_resnet_state_dict
         dev = torch.device(device if device is not None else "cuda")
@@ -175,6 +183,11 @@ class DiariZenPipeline:
             "clustering": {"args": {"method": "AgglomerativeClustering", "min_speakers": min_speakers, "max_speakers": max_speakers,
                                     "ahc_criterion": "distance", "ahc_threshold": ahc_threshold, "min_cluster_size": min_cluster_size}},
         }
+        if vbx is not None:
+            # vbx = {"plda_dir": ..., "Fa": ..., "Fb": ..., "lda_dim": ..., "max_iters": ...} switches to the VBx method
+            config["clustering"]["args"].update({"method": "VBxClustering", "Fa": 0.07, "Fb": 0.8, "lda_dim": 128,
+                                                 "max_iters": 20})
+            config["clustering"]["args"].update(vbx)
         return cls(None, None, rttm_out_dir=rttm_out_dir, precision=precision, device=dev, _seg=seg, _emb=emb, _config=config)
 
     # ------------------------------------------------------------------------------------------------

@@ -193,6 +193,14 @@ int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_
 /* per-chunk constrained assignment maximising the summed soft score (clustering.py:159-173); hard [C][S] int8, -2 = none */
 int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream);
 
+/* VBx: the two halves of one VB-GMM iteration over PLDA-space x-vectors, float64 (diarizen/clustering/VBx.py:86-111).
+ * rho = X * sqrt(Phi) [N][D]; G[t] = -0.5 * (|x_t|^2 + D log 2 pi); gamma [N][S]. */
+int dz_vbx_model(const double* gamma_dev, const double* rho_dev, const double* phi_dev, int N, int D, int S, double fa_over_fb,
+                 double* alpha_dev, double* invl_dev, void* stream);
+int dz_vbx_resp(const double* rho_dev, const double* g_dev, const double* alpha_dev, const double* invl_dev, const double* phi_dev,
+                const double* pi_dev, int N, int D, int S, double Fa, double* gamma_dev, double* pi_acc_dev, double* logpx_acc_dev,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

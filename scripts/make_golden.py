@@ -86,7 +86,34 @@ def main():
                 out[k + "_w"] = w.numpy()
             out[k + "_y"] = sp(xx, weights=w).numpy()
     np.savez_compressed(os.path.join(OUT, "stats_pool.npz"), **out)
+    make_vbx()
     print("golden fixtures written to", OUT)
+
+
+def make_vbx():
+    """VBx fixture through the reference's diarizen/clustering/VBx.py (vbx_setup + cluster_vbx) on a synthetic PLDA."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vbx_util
+    from oracle.pipeline_oracle import filter_embeddings
+    spec = importlib.util.spec_from_file_location("ref_vbx", os.path.join(ref_loader.REF, "diarizen/clustering/VBx.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    seed, Fa, Fb, iters, lda_dim = 5, 0.07, 0.8, 20, 128
+    emb, seg = vbx_util.make_embeddings(seed)
+    train, _, _ = filter_embeddings(emb, seg)
+    with tempfile.TemporaryDirectory() as d:
+        vbx_util.write_plda(d, seed)
+        x_tf, plda_tf, psi = ref.vbx_setup(d)
+    fea = plda_tf(x_tf(train), lda_dim=lda_dim)
+    labels = np.random.default_rng(seed).integers(0, 6, size=len(train))
+    from scipy.special import softmax
+    q0 = np.zeros((len(labels), labels.max() + 1))
+    q0[np.arange(len(labels)), labels] = 1.0
+    q0 = softmax(q0 * 7.0, axis=1)
+    gamma, pi = ref.cluster_vbx(labels, fea, psi[:lda_dim], Fa=Fa, Fb=Fb, maxIters=iters)
+    np.savez_compressed(os.path.join(OUT, "vbx.npz"), seed=seed, Fa=Fa, Fb=Fb, max_iters=iters, train=train, fea=fea,
+                        psi=psi, phi=psi[:lda_dim], labels=labels, q0=q0, gamma=gamma, pi=pi)
 
 
 if __name__ == "__main__":
