@@ -310,7 +310,8 @@ __global__ void assign_kernel(const double* __restrict__ soft, int C, int S, int
     // speaker 0 is the most significant digit: among equal totals the lexicographically smallest map wins, which is what
     // scipy's solver returns for the all-equal (NaN-filled) rows of inactive speakers
     for (int s = S - 1; s >= 0; --s) {
-      const int k = t % base - 1;
+      const int dgt = t % base;
+      const int k = dgt < K ? dgt : -1;     // "unassigned" sorts after every cluster
       t /= base;
       a[s] = k;
       if (k >= 0) {
