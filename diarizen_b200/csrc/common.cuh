@@ -32,26 +32,37 @@ DZ_DEVINL void mbar_arrive(uint64_t* bar) {
 }
 DZ_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the last operand is the suspend-time hint (ns): the warp may sleep in hardware until the phase flips instead of
+  // re-issuing the poll, which keeps the spin loops of the producer / issuer warps out of the math warps' issue slots
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.
+// Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.  The clock is sampled only
+// every 4096 polls so that the common path is poll + branch.
 DZ_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t n = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("dz: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
+    if ((++n & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("dz: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
+// dynamic shared memory rounded up to the 1024-byte alignment the 128-byte swizzle atoms need.  Pointer arithmetic (not an
+// integer round trip) so that the compiler keeps the shared address space and emits LDS/STS instead of generic LD/ST.
+DZ_DEVINL uint8_t* smem_align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 DZ_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -173,6 +184,9 @@ DZ_DEVINL void tmem_ld_32x32_x16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 DZ_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+DZ_DEVINL void tmem_st_32x32_x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 DZ_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "

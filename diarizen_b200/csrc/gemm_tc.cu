@@ -202,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmDesc d, const int 
                const int ntiles) {
   using C = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   float* patches = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES + C::PATCH_BYTES);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
@@ -428,7 +428,7 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
                    const int mt, const int nt, const int ntiles, const int mode) {
   using C = TcCfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* patches = smem + C::NSTAGE * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(patches + NUM_EPI2 * C::PATCH);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
