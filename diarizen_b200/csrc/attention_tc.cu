@@ -251,6 +251,7 @@ DZ_DEVINL uint32_t pack16(float lo, float hi, int fp16) {
   return r;
 }
 
+template <int FP16>
 __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a,
                                                                      const int B) {
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
   if (warp == 5) tmem_alloc(tmem_ptr, 256);
   {
     // constant tail of every V stage: row 64 = ones (swizzle phase 0: stored as is), rows 65..79 = zeros
-    const uint32_t one2 = a.fp16 ? 0x3C003C00u : 0x3F803F80u;
+    const uint32_t one2 = FP16 ? 0x3C003C00u : 0x3F803F80u;
     for (int i = threadIdx.x; i < KV_STAGES * 512; i += A_THREADS) {
       const int s = i >> 9, wd = i & 511;
       reinterpret_cast<uint32_t*>(Vs + s * V_STAGE_BYTES + 8192)[wd] = wd < 32 ? one2 : 0u;
@@ -327,8 +328,8 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 64, a.fp16);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 80, a.fp16);
+      const uint32_t idesc_s = umma_idesc_bf16(128, 64, FP16);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 80, FP16);
       const uint32_t qa = smem_u32(Qs);
       uint32_t g = 0, n = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
@@ -374,7 +375,6 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
     const int row = threadIdx.x;  // 0..127
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const int sw = row & 7;
-    const int fp16 = a.fp16;
     uint32_t g = 0, n = 0;
     int cur_h = -1;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
         for (int c8 = 0; c8 < 8; ++c8) {
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack16(ex2(r[8 * c8 + 2 * e]), ex2(r[8 * c8 + 2 * e + 1]), fp16);
+          for (int e = 0; e < 4; ++e) w[e] = pack2_16<FP16>(ex2(r[8 * c8 + 2 * e]), ex2(r[8 * c8 + 2 * e + 1]));
           *reinterpret_cast<uint4*>(prow + ((c8 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             bf16 h0, l0, h1, l1;
-            split_bf16(__uint_as_float(o[8 * c8 + 2 * e]) * inv, h0, l0, a.fp16);
-            split_bf16(__uint_as_float(o[8 * c8 + 2 * e + 1]) * inv, h1, l1, a.fp16);
+            split_bf16(__uint_as_float(o[8 * c8 + 2 * e]) * inv, h0, l0, FP16);
+            split_bf16(__uint_as_float(o[8 * c8 + 2 * e + 1]) * inv, h1, l1, FP16);
             hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
           }
@@ -536,8 +536,9 @@ cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
   static size_t attr = 0;
   const bool v1 = attn_use_v1();
   if (p->smem > attr) {
-    cudaError_t e = v1 ? cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)
-                       : cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e != cudaSuccess) return e;
     attr = p->smem;
   }
@@ -553,7 +554,9 @@ cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
       slots = 2 * sms;   // two resident CTAs per SM (launch bounds, 110 KB of shared memory and 256 TMEM columns each)
     }
     const long long items = (long long)grid.x * grid.y * grid.z;
-    attention_tc2_kernel<<<(unsigned)(items < slots ? items : slots), A_THREADS, p->smem, st>>>(p->maps, p->a, p->B);
+    const unsigned g = (unsigned)(items < slots ? items : slots);
+    if (p->a.fp16) attention_tc2_kernel<1><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B);
+    else attention_tc2_kernel<0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B);
   }
   return cudaGetLastError();
 }

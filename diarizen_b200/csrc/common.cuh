@@ -243,6 +243,14 @@ DZ_DEVINL void split_bf16(float x, bf16& hi, bf16& lo, int fp16) {
   hi = to16(x, fp16);
   lo = to16(x - from16(hi, fp16), fp16);
 }
+// two fp32 -> one packed pair of 16-bit operands (lo in the low half); the fp16 flavour saturates like to16()
+template <int FP16>
+DZ_DEVINL uint32_t pack2_16(float lo, float hi) {
+  uint32_t r;
+  if (FP16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 DZ_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -402,6 +402,51 @@ DZ_DEVINL float4 unpack4(uint2 w, int fp16) {
   return q;
 }
 
+// One 32-column group of one accumulator row -> 16-bit (hi [+ lo]) cells of the swizzled store patch; the 16-bit residual
+// (TMA-prefetched into the same cells) is added first.  FP16 / TWO are compile-time so that the per-element conversions
+// carry no branches (a uniform run-time flag still costs a branch per element once the loop is unrolled).
+template <int FP16, int TWO>
+DZ_DEVINL void epi_store16(uint8_t* prow, int g, int sw, const float* v, bool has_res, bool relu_after, int nrem) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {   // 4 x 16-byte chunks of 8 columns; chunk index within the 64-column row = 4g + h
+    uint4* chi = reinterpret_cast<uint4*>(prow + (((4 * g + h) ^ sw) << 4));
+    uint4* clo = reinterpret_cast<uint4*>(prow + 4096 + (((4 * g + h) ^ sw) << 4));
+    float e[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = v[8 * h + c];
+    if (has_res) {
+      const uint4 rh = *chi;
+      float4 r0 = unpack4(make_uint2(rh.x, rh.y), FP16), r1 = unpack4(make_uint2(rh.z, rh.w), FP16);
+      if (TWO) {
+        const uint4 rl = *clo;
+        const float4 l0 = unpack4(make_uint2(rl.x, rl.y), FP16), l1 = unpack4(make_uint2(rl.z, rl.w), FP16);
+        r0.x += l0.x; r0.y += l0.y; r0.z += l0.z; r0.w += l0.w;
+        r1.x += l1.x; r1.y += l1.y; r1.z += l1.z; r1.w += l1.w;
+      }
+      e[0] += r0.x; e[1] += r0.y; e[2] += r0.z; e[3] += r0.w; e[4] += r1.x; e[5] += r1.y; e[6] += r1.z; e[7] += r1.w;
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float x0 = e[2 * c], x1 = e[2 * c + 1];
+      if (relu_after) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (8 * h + 2 * c >= nrem) x0 = 0.f;
+      if (8 * h + 2 * c + 1 >= nrem) x1 = 0.f;
+      if (TWO) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(x0, h0, l0, FP16);
+        split_bf16(x1, h1, l1, FP16);
+        hw[c] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[c] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      } else {
+        hw[c] = pack2_16<FP16>(x0, x1);
+      }
+    }
+    *chi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (TWO) *clo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // bias + pre-residual activation + scale on 32 accumulator columns held in registers (one code block per activation)
 template <int ACT>
 DZ_DEVINL void epi_math32(float (&v)[32], const float* __restrict__ bias, float alpha) {
@@ -612,39 +657,12 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
               *cell = o;
             }
           } else {
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {   // 4 x 16-byte chunks of 8 columns; chunk index within the 64-column row = 4g + h
-              uint4* chi = reinterpret_cast<uint4*>(prow + (((4 * g + h) ^ sw) << 4));
-              uint4* clo = reinterpret_cast<uint4*>(prow + 4096 + (((4 * g + h) ^ sw) << 4));
-              float e[8];
-#pragma unroll
-              for (int c = 0; c < 8; ++c) e[c] = v[8 * h + c];
-              if (has_res) {
-                const uint4 rh = *chi;
-                float4 r0 = unpack4(make_uint2(rh.x, rh.y), fp16), r1 = unpack4(make_uint2(rh.z, rh.w), fp16);
-                if (two) {
-                  const uint4 rl = *clo;
-                  const float4 l0 = unpack4(make_uint2(rl.x, rl.y), fp16), l1 = unpack4(make_uint2(rl.z, rl.w), fp16);
-                  r0.x += l0.x; r0.y += l0.y; r0.z += l0.z; r0.w += l0.w;
-                  r1.x += l1.x; r1.y += l1.y; r1.z += l1.z; r1.w += l1.w;
-                }
-                e[0] += r0.x; e[1] += r0.y; e[2] += r0.z; e[3] += r0.w; e[4] += r1.x; e[5] += r1.y; e[6] += r1.z; e[7] += r1.w;
-              }
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float x0 = e[2 * c], x1 = e[2 * c + 1];
-                if (relu_after) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                if (8 * h + 2 * c >= nrem) x0 = 0.f;
-                if (8 * h + 2 * c + 1 >= nrem) x1 = 0.f;
-                bf16 h0, l0, h1, l1;
-                split_bf16(x0, h0, l0, fp16);
-                split_bf16(x1, h1, l1, fp16);
-                hw[c] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[c] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-              }
-              *chi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (two) *clo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            const int variant = (fp16 ? 1 : 0) | (two ? 2 : 0);
+            switch (variant) {
+              case 0: epi_store16<0, 0>(prow, g, sw, v, has_res, relu_after, nrem); break;
+              case 1: epi_store16<1, 0>(prow, g, sw, v, has_res, relu_after, nrem); break;
+              case 2: epi_store16<0, 1>(prow, g, sw, v, has_res, relu_after, nrem); break;
+              default: epi_store16<1, 1>(prow, g, sw, v, has_res, relu_after, nrem); break;
             }
           }
         }
