@@ -79,6 +79,7 @@ class AttnArgs(C.Structure):
         ("vt", C.c_void_p), ("vt_plane", C.c_int64), ("ldvt", C.c_int32), ("planes", C.c_int32),
         ("bias_tab", C.c_void_p), ("gate", C.c_void_p),
         ("out", C.c_void_p), ("out_plane", C.c_int64), ("ldo", C.c_int32), ("out_planes", C.c_int32),
+        ("v", C.c_void_p), ("v_col", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

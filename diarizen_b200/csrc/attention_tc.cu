@@ -251,7 +251,7 @@ DZ_DEVINL uint32_t pack16(float lo, float hi, int fp16) {
   return r;
 }
 
-template <int FP16>
+template <int FP16, int VROW>
 __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a,
                                                                      const int B) {
   extern __shared__ uint8_t smem_raw[];
@@ -259,7 +259,12 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
   uint8_t* Qs = smem;                              // 128 x 64, SW128
   uint8_t* Ks = Qs + 16384;                        // KV_STAGES x (64 keys x 64 d)
   uint8_t* Vs = Ks + KV_STAGES * 8192;             // KV_STAGES x (80 rows x 64 keys): 64 d rows + ones row + 15 zero rows
-  uint8_t* Ps = Vs + KV_STAGES * V_STAGE_BYTES;    // 2 x (128 x 64), SW128
+  // VROW: V arrives row-major (64 keys x 64 d per stage, MN-major B operand) and the ones column lives in one shared 8 KB
+  // constant block after the stages (second 64-wide N chunk, reached through the descriptor's leading byte offset)
+  constexpr int VST = VROW ? 8192 : V_STAGE_BYTES;
+  constexpr int VTOT = VROW ? KV_STAGES * 8192 + 8192 : KV_STAGES * V_STAGE_BYTES;
+  uint8_t* Vc = Vs + KV_STAGES * 8192;
+  uint8_t* Ps = Vs + VTOT;                         // 2 x (128 x 64), SW128
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 16384);
   uint64_t* q_full = bars;
   uint64_t* q_empty = bars + 1;
@@ -297,9 +302,17 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
   {
     // constant tail of every V stage: row 64 = ones (swizzle phase 0: stored as is), rows 65..79 = zeros
     const uint32_t one2 = FP16 ? 0x3C003C00u : 0x3F803F80u;
-    for (int i = threadIdx.x; i < KV_STAGES * 512; i += A_THREADS) {
-      const int s = i >> 9, wd = i & 511;
-      reinterpret_cast<uint32_t*>(Vs + s * V_STAGE_BYTES + 8192)[wd] = wd < 32 ? one2 : 0u;
+    if (VROW) {
+      // row r (key) of the constant block: column 0 = 1, columns 1..63 = 0; column 0 sits in 16-byte chunk (0 ^ (r & 7))
+      for (int i = threadIdx.x; i < 2048; i += A_THREADS) {
+        const int r = i >> 5, wd = i & 31;
+        reinterpret_cast<uint32_t*>(Vc)[i] = (wd == ((r & 7) << 2)) ? (one2 & 0xFFFFu) : 0u;
+      }
+    } else {
+      for (int i = threadIdx.x; i < KV_STAGES * 512; i += A_THREADS) {
+        const int s = i >> 9, wd = i & 511;
+        reinterpret_cast<uint32_t*>(Vs + s * V_STAGE_BYTES + 8192)[wd] = wd < 32 ? one2 : 0u;
+      }
     }
     fence_proxy_async();
   }
@@ -322,14 +335,15 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
           if (use > 0) mbar_wait(&kv_empty[s], (use - 1) & 1);
           mbar_expect_tx(&kv_full[s], 16384);
           tma_load_3d(Ks + s * 8192, &maps.k, &kv_full[s], a.k_col + hi * 64, j * ABK, b);
-          tma_load_3d(Vs + s * V_STAGE_BYTES, &maps.vt, &kv_full[s], j * ABK, hi * 64, b);
+          if (VROW) tma_load_3d(Vs + s * VST, &maps.vt, &kv_full[s], a.v_col + hi * 64, j * ABK, b);
+          else tma_load_3d(Vs + s * VST, &maps.vt, &kv_full[s], j * ABK, hi * 64, b);
         }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 64, FP16);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 80, FP16);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 80, FP16) | (VROW ? (1u << 16) : 0u);   // bit 16: B is MN-major
       const uint32_t qa = smem_u32(Qs);
       uint32_t g = 0, n = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
@@ -360,10 +374,17 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
           mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
           if (j == 0 && n > 0) mbar_wait(o_free, (n - 1) & 1);   // the previous item's O has been read out of TMEM
           tc_fence_after();
-          const uint32_t pa = smem_u32(Ps + (g & 1) * 16384), va = smem_u32(Vs + s * V_STAGE_BYTES);
+          const uint32_t pa = smem_u32(Ps + (g & 1) * 16384), va = smem_u32(Vs + s * VST);
+          if (VROW) {
+            const uint32_t lbo = smem_u32(Vc) - va;   // first N chunk (d 0..63) -> second chunk (ones column + 15 zeros)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128(va + k * 32), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)   // 16 keys = 16 rows of 128 B per step
+              umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128_mn(va + k * 2048, lbo), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128(va + k * 32), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&kv_empty[s]);
           umma_commit(o_ready);
         }
@@ -507,6 +528,7 @@ static bool attn_use_v1() {
 }
 
 AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B) {
+  if (attn_use_v1() && a.v != nullptr) return nullptr;   // the first-generation kernel only takes the transposed V
   AttnPlan* p = new AttnPlan();
   p->a = a;
   p->B = B;
@@ -520,14 +542,20 @@ AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B) {
       return nullptr;
     }
   }
-  {
+  if (a.v != nullptr) {
+    uint64_t dims[3] = {(uint64_t)a.ldqk, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {1, (uint64_t)a.ldqk, (uint64_t)T * a.ldqk};
+    uint32_t box[3] = {64, ABK, 1};
+    if (!make_tmap_bf16(&p->maps.vt, a.v, 3, dims, str, box)) { delete p; return nullptr; }
+  } else {
     uint64_t dims[3] = {(uint64_t)T, (uint64_t)a.nheads * 64, (uint64_t)B};
     uint64_t str[3] = {1, (uint64_t)a.ldvt, (uint64_t)a.nheads * 64 * a.ldvt};
     uint32_t box[3] = {ABK, 64, 1};
     if (!make_tmap_bf16(&p->maps.vt, a.vt, 3, dims, str, box)) { delete p; return nullptr; }
   }
   if (attn_use_v1()) p->smem = 1024 + 16384 + 2 * 8192 + 2 * 8192 + 16384 + 80 + sizeof(float) * (size_t)(2 * T - 1 + 64 + 8);
-  else p->smem = 1024 + 16384 + KV_STAGES * 8192 + KV_STAGES * V_STAGE_BYTES + 2 * 16384 + 128 + sizeof(float) * (size_t)(2 * T - 1 + 64 + 8);
+  else p->smem = 1024 + 16384 + KV_STAGES * 8192 + (a.v != nullptr ? KV_STAGES * 8192 + 8192 : KV_STAGES * V_STAGE_BYTES) + 2 * 16384 + 128 +
+                 sizeof(float) * (size_t)(2 * T - 1 + 64 + 8);
   return p;
 }
 void attention_tc_plan_destroy(AttnPlan* p) { delete p; }
@@ -537,8 +565,10 @@ cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
   const bool v1 = attn_use_v1();
   if (p->smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e != cudaSuccess) return e;
     attr = p->smem;
   }
@@ -555,8 +585,13 @@ cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
     }
     const long long items = (long long)grid.x * grid.y * grid.z;
     const unsigned g = (unsigned)(items < slots ? items : slots);
-    if (p->a.fp16) attention_tc2_kernel<1><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B);
-    else attention_tc2_kernel<0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B);
+    const int variant = (p->a.fp16 ? 1 : 0) | (p->a.v != nullptr ? 2 : 0);
+    switch (variant) {
+      case 0: attention_tc2_kernel<0, 0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
+      case 1: attention_tc2_kernel<1, 0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
+      case 2: attention_tc2_kernel<0, 1><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
+      default: attention_tc2_kernel<1, 1><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
+    }
   }
   return cudaGetLastError();
 }

@@ -137,6 +137,17 @@ DZ_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
 }
+// MN-major operand (the N or M index is the contiguous one), 128-byte swizzle: one row per K index holding 64 MN elements
+// (128 B); 8-row K groups `SBO` = 1024 B apart; the next block of 64 MN elements `lbo_bytes` after the first.
+DZ_DEVINL uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 accumulate.
 DZ_DEVINL uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, int fp16 = 0) {
   uint32_t d = 0;

@@ -471,8 +471,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
   float* xres = p.buf((size_t)R * Dp * 4 + 256, true)->as<float>();
   float* mix = p.buf((size_t)R * Dp * 4 + 256, true)->as<float>();
   Planes xbf = p.planes((size_t)R * std::max(Dp, Cp[6]) + 64, true);
-  Planes qk = p.planes((size_t)R * 2 * hmax * 64 + 64, true);
-  Planes vt = p.planes((size_t)B * hmax * 64 * Tp + 64, true);
+  Planes qk = p.planes((size_t)R * 3 * hmax * 64 + 64, true);   // q | k | v columns of every frame row
   Planes ctx = p.planes((size_t)R * hmax * 64 + 64, true);
   Planes mid = p.planes((size_t)R * Fp + 64, true);
   float* gate = p.buf((size_t)B * hmax * T * 4 + 64, true)->as<float>();
@@ -535,12 +534,13 @@ static int plan_impl(dz_seg* s, int B, int N) {
   auto attention = [&](const std::string& nm, Planes xin, int ldx, const Weight& Wqkv, const Weight& Wo, int h,
                        const float* tab, const float* gatep, float* resid, int ldres) {
     GemmDesc d = p.linear(xin, ldx, R, Wqkv);
-    d.out_bf = qk.p; d.ob_plane = qk.plane; d.ldob = 2 * h * 64;
-    d.out_t = vt.p; d.ot_plane = vt.plane; d.ot_bstride = (long long)h * 64 * Tp; d.ldt = Tp; d.tr_col0 = 2 * h * 64; d.seq_len = T;
+    // one plain GEMM: V stays row-major next to q and k (the attention kernel takes it as an MN-major operand), so the
+    // projection needs no transposing epilogue
+    d.out_bf = qk.p; d.ob_plane = qk.plane; d.ldob = 3 * h * 64;
     p.gemm(nm + "_qkv", d);
     AttnArgs at{};
-    at.T = T; at.nheads = h; at.q = qk.p; at.k = qk.p; at.qk_plane = qk.plane; at.ldqk = 2 * h * 64; at.q_col = 0; at.k_col = h * 64;
-    at.vt = vt.p; at.vt_plane = vt.plane; at.ldvt = Tp; at.planes = P; at.bias_tab = tab; at.gate = gatep;
+    at.T = T; at.nheads = h; at.q = qk.p; at.k = qk.p; at.qk_plane = qk.plane; at.ldqk = 3 * h * 64; at.q_col = 0; at.k_col = h * 64;
+    at.v = qk.p; at.v_col = 2 * h * 64; at.planes = P; at.bias_tab = tab; at.gate = gatep;
     at.out = ctx.p; at.out_plane = ctx.plane; at.ldo = h * 64; at.out_planes = P; at.fp16 = FP;
     // the tensor-core attention kernel multiplies the hi planes only; the fp32-class mode uses the CUDA-core kernel
     const int impl = (s->npass == 3) ? 1 : s->attn_impl;

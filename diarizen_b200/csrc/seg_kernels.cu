@@ -522,9 +522,15 @@ __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
       const int d = i >> 6, j = i & 63;
       float v = 0.f;
       if (k0 + j < T) {
-        const bf16* vp = a.vt + ((long long)b * a.nheads * 64 + hi * 64 + d) * a.ldvt + k0 + j;
-        v = from16(*vp, a.fp16);
-        if (two) v += from16(vp[a.vt_plane], a.fp16);
+        if (a.v != nullptr) {
+          const bf16* vp = a.v + ((long long)b * T + k0 + j) * a.ldqk + a.v_col + hi * 64 + d;
+          v = from16(*vp, a.fp16);
+          if (two) v += from16(vp[a.qk_plane], a.fp16);
+        } else {
+          const bf16* vp = a.vt + ((long long)b * a.nheads * 64 + hi * 64 + d) * a.ldvt + k0 + j;
+          v = from16(*vp, a.fp16);
+          if (two) v += from16(vp[a.vt_plane], a.fp16);
+        }
       }
       Vs[i] = v;
     }

@@ -44,6 +44,7 @@ struct AttnArgs {   // layout mirrors dz_attn_args (include/diarizen_b200.h)
   const float* bias_tab;   // [nheads][2T-1] or null
   const float* gate;       // [B][nheads][T] or null
   __nv_bfloat16* out; long long out_plane; int ldo; int out_planes;  // [B*T][ldo]
+  const __nv_bfloat16* v; int v_col; int _pad;   // optional row-major V [B*T][ldqk] (planes qk_plane apart); replaces vt when set
 };
 
 struct DwArgs {

@@ -99,6 +99,8 @@ typedef struct dz_attn_args {
   const void* vt; int64_t vt_plane; int32_t ldvt, planes;
   const float* bias_tab; const float* gate;
   void* out; int64_t out_plane; int32_t ldo, out_planes;
+  const void* v; int32_t v_col, _pad;   /* optional: V row-major [B*T][ldqk] at column v_col + head*64 (same plane stride as q/k);
+                                           when set it replaces the transposed vt (no transposing producer needed) */
 } dz_attn_args;
 int dz_attention(const dz_attn_args* a, int B, int impl, void* stream);
 

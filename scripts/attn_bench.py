@@ -19,7 +19,8 @@ torch.manual_seed(0)
 q = torch.randn(B, T, h, 64, device=dev) * 0.5
 k = torch.randn(B, T, h, 64, device=dev)
 v = torch.randn(B, T, h, 64, device=dev)
-qkp = to_planes(torch.cat([q.reshape(B * T, h * 64), k.reshape(B * T, h * 64)], dim=1))
+VROW = os.environ.get("DZ_ATTN_VT", "0") != "1"
+qkp = to_planes(torch.cat([q.reshape(B * T, h * 64), k.reshape(B * T, h * 64)] + ([v.reshape(B * T, h * 64)] if VROW else []), dim=1))
 Tp = rup(T, 8)
 vtp = to_planes(v.permute(0, 2, 3, 1).reshape(B, h * 64, T), Tp)
 tab = torch.randn(h, 2 * T - 1, device=dev)
@@ -28,8 +29,12 @@ out = torch.zeros(2, B * T, h * 64, device=dev, dtype=torch.bfloat16)
 a = _lib.AttnArgs()
 a.T, a.nheads = T, h
 a.q = a.k = ptr(qkp).value
-a.qk_plane, a.ldqk, a.q_col, a.k_col = qkp[0].numel(), 2 * h * 64, 0, h * 64
-a.vt, a.vt_plane, a.ldvt, a.planes = ptr(vtp).value, vtp[0].numel(), Tp, 1
+a.qk_plane, a.ldqk, a.q_col, a.k_col = qkp[0].numel(), (3 if VROW else 2) * h * 64, 0, h * 64
+a.planes = 1
+if VROW:
+    a.v, a.v_col = ptr(qkp).value, 2 * h * 64
+else:
+    a.vt, a.vt_plane, a.ldvt = ptr(vtp).value, vtp[0].numel(), Tp
 a.bias_tab, a.gate = ptr(tab).value, ptr(gate).value
 a.out, a.out_plane, a.ldo, a.out_planes = ptr(out).value, out[0].numel(), h * 64, 1
 L = _lib.lib()
@@ -44,7 +49,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 fl = 4.0 * B * h * T * T * 64
-print(f"attention B={B} T={T} h={h} v1={os.environ.get('DZ_ATTN_V1', '0')}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TF/s", flush=True)
+print(f"attention B={B} T={T} h={h} vrow={int(VROW)}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TF/s", flush=True)
 # correctness spot check against fp64 torch on window 0 / head 0
 qv = qkp[0].double()[:T, :64]
 kv = qkp[0].double()[:T, h * 64:h * 64 + 64]

@@ -11,16 +11,18 @@ from gpu_util import ptr, rup, to_planes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("vrow", [0, 1], ids=["vT", "vrow"])
 @pytest.mark.parametrize("impl", [0, 1], ids=["tc", "simt"])
-@pytest.mark.parametrize("B,T,h,bias", [(2, 49, 1, True), (2, 249, 3, True), (1, 799, 2, True), (2, 130, 4, False), (1, 64, 1, True)])
-def test_attention(impl, B, T, h, bias):
+@pytest.mark.parametrize("B,T,h,bias", [(2, 49, 1, True), (2, 249, 3, True), (1, 799, 2, True), (2, 130, 4, False), (1, 64, 1, True),
+                                        (3, 799, 5, True)])
+def test_attention(impl, B, T, h, bias, vrow):
     torch.manual_seed(T + h)
     dev = "cuda"
     q = torch.randn(B, T, h, 64, device=dev) * 0.5
     k = torch.randn(B, T, h, 64, device=dev)
     v = torch.randn(B, T, h, 64, device=dev)
-    qk = torch.cat([q.reshape(B * T, h * 64), k.reshape(B * T, h * 64)], dim=1)
-    qkp = to_planes(qk)
+    cols = [q.reshape(B * T, h * 64), k.reshape(B * T, h * 64)] + ([v.reshape(B * T, h * 64)] if vrow else [])
+    qkp = to_planes(torch.cat(cols, dim=1))
     Tp = rup(T, 8)
     vtp = to_planes(v.permute(0, 2, 3, 1).reshape(B, h * 64, T), Tp)
     planes = 2 if impl == 1 else 1
@@ -30,8 +32,12 @@ def test_attention(impl, B, T, h, bias):
     a = _lib.AttnArgs()
     a.T, a.nheads = T, h
     a.q = a.k = ptr(qkp).value
-    a.qk_plane, a.ldqk, a.q_col, a.k_col = qkp[0].numel(), 2 * h * 64, 0, h * 64
-    a.vt, a.vt_plane, a.ldvt, a.planes = ptr(vtp).value, vtp[0].numel(), Tp, planes
+    a.qk_plane, a.ldqk, a.q_col, a.k_col = qkp[0].numel(), (3 if vrow else 2) * h * 64, 0, h * 64
+    a.planes = planes
+    if vrow:   # V row-major next to q | k (what the engine's single QKV projection writes)
+        a.v, a.v_col = ptr(qkp).value, 2 * h * 64
+    else:
+        a.vt, a.vt_plane, a.ldvt = ptr(vtp).value, vtp[0].numel(), Tp
     a.bias_tab = ptr(tab).value if bias else None
     a.gate = ptr(gate).value if bias else None
     a.out, a.out_plane, a.ldo, a.out_planes = ptr(out).value, out[0].numel(), h * 64, 2
@@ -42,7 +48,7 @@ def test_attention(impl, B, T, h, bias):
         x = p[0].double()
         return x + p[1].double() if planes == 2 else x
     qv = val(qkp)[:, :h * 64].view(B, T, h, 64).permute(0, 2, 1, 3)
-    kv = val(qkp)[:, h * 64:].view(B, T, h, 64).permute(0, 2, 1, 3)
+    kv = val(qkp)[:, h * 64:2 * h * 64].view(B, T, h, 64).permute(0, 2, 1, 3)
     vv = val(vtp)[..., :T].view(B, h, 64, T).permute(0, 1, 3, 2)
     s = qv @ kv.transpose(-1, -2)
     if bias:
