@@ -227,7 +227,21 @@ DZ_DEVINL float erf_as(float z) {
   const float e = 1.0f - p * t * __expf(-a * a);
   return copysignf(e, z);
 }
-DZ_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+// gelu(x) = x * Phi(x) with the same A-S polynomial folded through: Phi(x) = h for x < 0 and 1 - h for x >= 0, where
+// h = 0.5 * P(t) * exp(-x^2 / 2), t = 1 / (1 + 0.3275911 |x| / sqrt(2)).  12 FP32 ops + RCP + EX2 per element.
+DZ_DEVINL float gelu_erf(float x) {
+  float t, e;
+  const float d = fmaf(0.23164189f, fabsf(x), 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(d));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float xx = x * x;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xx * -0.72134752044448170368f));   // exp(-x^2 / 2)
+  const float xh = x * (p * t * e);
+  return x > 0.0f ? x - xh : xh;
+}
 DZ_DEVINL float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 DZ_DEVINL float apply_act(float x, int act) {
   switch (act) {

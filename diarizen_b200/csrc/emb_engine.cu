@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include "../../include/diarizen_b200.h"
 #include "common.cuh"
 #include "emb_kernels.h"
@@ -42,6 +43,7 @@ struct dz_emb {
   int B = 0, N = 0, S = 0, T = 0, F = 0;
   std::vector<Step> steps;
   std::vector<GemmPlan*> plans;
+  std::vector<Conv3Plan*> c3plans;
   std::vector<DevMem*> ws;
   DevMem widx;
   const float* cur_wav = nullptr; const float* cur_masks = nullptr; float* cur_out = nullptr;
@@ -52,6 +54,8 @@ struct dz_emb {
   void clear_plan() {
     for (auto* p : plans) gemm_plan_destroy(p);
     plans.clear();
+    for (auto* p : c3plans) conv3x3_c32_plan_destroy(p);
+    c3plans.clear();
     for (auto* w : ws) delete w;
     ws.clear();
     steps.clear();
@@ -254,6 +258,18 @@ static int emb_plan(dz_emb* s, int B, int N, int S, int T) {
     const double flops = 2.0 * B * Ho * Wo * (double)Cout * ks * ks * Cin;
     if (s->gemm_impl == 1) {
       s->steps.push_back({nm, [d](cudaStream_t st) { return gemm_simt_launch(d, st); }, flops, 0.0});
+      return;
+    }
+    static const bool c3_off = [] { const char* e = getenv("DZ_CONV3_GENERIC"); return e && e[0] == '1'; }();
+    if (!c3_off && ks == 3 && stride == 1 && Cin == 32 && Cout == 32 && P == 1 && s->npass == 1 && act == 3) {
+      // layer1: resident weights + row-shifted A views instead of the generic implicit GEMM (conv3x3_c32.cu)
+      Conv3Args c{};
+      c.in = in.p; c.out = out.p; c.res = res ? res->p : nullptr; c.w = W.w.as<bf16>(); c.ldw = W.ldb; c.bias = W.bias.as<float>();
+      c.B = B; c.H = Hin; c.W = Win; c.relu = 1; c.fp16 = FP;
+      Conv3Plan* cp = conv3x3_c32_plan_create(c);
+      if (!cp) { if (!err) { err = DZ_ERR_CUDA; msg = "conv3x3 plan '" + nm + "': " + gemm_last_error(); } return; }
+      s->c3plans.push_back(cp);
+      s->steps.push_back({nm, [cp](cudaStream_t st) { return conv3x3_c32_plan_launch(cp, st); }, flops, 0.0});
       return;
     }
     GemmPlan* p = gemm_plan_create(d, 0);

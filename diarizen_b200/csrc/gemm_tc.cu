@@ -758,6 +758,34 @@ bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
   return true;
 }
 
+// 16-bit tensor map with a selectable swizzle span (32 / 64 / 128 bytes); used by the small-channel convolution kernel
+bool make_tmap_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                  const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { g_err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_elems[i] * 2;
+      if (gstr[i - 1] % 16 != 0) { g_err = "tensor map stride not a multiple of 16 bytes"; return false; }
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) { g_err = "tensor map base not 16-byte aligned"; return false; }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 struct GemmPlan {
   GemmDesc d;
   TcMaps maps;
