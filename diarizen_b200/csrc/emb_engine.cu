@@ -261,11 +261,11 @@ static int emb_plan(dz_emb* s, int B, int N, int S, int T) {
       return;
     }
     static const bool c3_off = [] { const char* e = getenv("DZ_CONV3_GENERIC"); return e && e[0] == '1'; }();
-    if (!c3_off && ks == 3 && stride == 1 && Cin == 32 && Cout == 32 && P == 1 && s->npass == 1 && act == 3) {
-      // layer1: resident weights + row-shifted A views instead of the generic implicit GEMM (conv3x3_c32.cu)
+    if (!c3_off && ks == 3 && stride == 1 && Cin == Cout && (Cin == 32 || Cin == 64) && P == 1 && s->npass == 1 && act == 3) {
+      // layer1 / layer2: resident weights + row-shifted A views instead of the generic implicit GEMM (conv3x3_c32.cu)
       Conv3Args c{};
       c.in = in.p; c.out = out.p; c.res = res ? res->p : nullptr; c.w = W.w.as<bf16>(); c.ldw = W.ldb; c.bias = W.bias.as<float>();
-      c.B = B; c.H = Hin; c.W = Win; c.relu = 1; c.fp16 = FP;
+      c.B = B; c.H = Hin; c.W = Win; c.relu = 1; c.fp16 = FP; c.C = Cin;
       Conv3Plan* cp = conv3x3_c32_plan_create(c);
       if (!cp) { if (!err) { err = DZ_ERR_CUDA; msg = "conv3x3 plan '" + nm + "': " + gemm_last_error(); } return; }
       s->c3plans.push_back(cp);

@@ -32,12 +32,12 @@ cudaError_t launch_fbank(const FbankArgs& a, int B, cudaStream_t st);
 cudaError_t launch_fbank_mean(const float* fb, int B, int F, float* mean, cudaStream_t st);
 cudaError_t launch_emb_conv1(const Conv1Args& a, cudaStream_t st);
 cudaError_t launch_stats_pool(const PoolArgs& a, int B, cudaStream_t st);
-// 3x3 / stride 1 / pad 1, 32 -> 32 channels (conv3x3_c32.cu).  in/out/res: zero-bordered NHWC planes [B][H][W+2][32];
-// w: the GEMM B matrix of the same layer, [32][ldw] with element (kh, kw, ci) at kh*128 + kw*32 + ci; bias [32].
+// 3x3 / stride 1 / pad 1, C -> C channels with C = 32 or 64 (conv3x3_c32.cu).  in/out/res: zero-bordered NHWC planes
+// [B][H][W+2][C]; w: the GEMM B matrix of the same layer, [C][ldw] with element (kh, kw, ci) at kh*rup(3C,64) + kw*C + ci.
 struct Conv3Args {
   const __nv_bfloat16* in; __nv_bfloat16* out; const __nv_bfloat16* res;
   const __nv_bfloat16* w; int ldw; const float* bias;
-  int B; int H; int W; int relu; int fp16;
+  int B; int H; int W; int relu; int fp16; int C;
 };
 struct Conv3Plan;
 Conv3Plan* conv3x3_c32_plan_create(const Conv3Args& a);
