@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include "../../include/diarizen_b200.h"
 #include "common.cuh"
 #include "gemm.h"
@@ -72,6 +73,7 @@ struct dz_seg {
   std::map<std::string, Tap> taps;
   std::vector<GemmPlan*> plans;
   std::vector<AttnPlan*> aplans;
+  std::vector<PosConvPlan*> pcplans;
   std::vector<DevMem*> ws;  // workspace buffers
   DevMem bias_tab;
   const float* cur_wav = nullptr;
@@ -100,6 +102,8 @@ struct dz_seg {
     plans.clear();
     for (auto* p : aplans) attention_tc_plan_destroy(p);
     aplans.clear();
+    for (auto* p : pcplans) posconv_plan_destroy(p);
+    pcplans.clear();
     for (auto* w : ws) delete w;
     ws.clear();
     steps.clear();
@@ -505,7 +509,20 @@ static int plan_impl(dz_seg* s, int B, int N) {
     d.bias = W.bias.as<float>(); d.act = 1; d.group_cols = Dg;
     d.residual = xres; d.res_bstride = (long long)T * Dp; d.ldr = Dp;
     d.out_f32 = xres; d.of_bstride = (long long)T * Dp; d.ldo = Dp;
-    p.gemm("pos_conv", d);
+    static const bool pc_generic = [] { const char* e = getenv("DZ_POSCONV_GENERIC"); return e && e[0] == '1'; }();
+    if (!pc_generic && s->npass == 1 && s->gemm_impl == 0 && Dg % 4 == 0) {
+      PosConvArgs pa{};
+      pa.stage = stage.p; pa.stage_rows = PCR; pa.stage_ld = PCW; pa.w = W.w.as<bf16>(); pa.ldw = W.ldb; pa.w_gstride = W.gstride;
+      pa.bias = W.bias.as<float>(); pa.x = xres; pa.ldx = Dp; pa.B = B; pa.T = T; pa.Dg = Dg; pa.fp16 = FP;
+      PosConvPlan* pp = posconv_plan_create(pa);
+      if (!pp) { if (!p.err) { p.err = DZ_ERR_CUDA; p.msg = std::string("pos-conv plan: ") + gemm_last_error(); } }
+      else {
+        s->pcplans.push_back(pp);
+        p.step("pos_conv", [pp](cudaStream_t st) { return posconv_plan_launch(pp, st); }, 2.0 * (double)R * D * 128 * Dg);
+      }
+    } else {
+      p.gemm("pos_conv", d);
+    }
   }
   const std::vector<float>& mw = s->mix_w;
   if (!large) {

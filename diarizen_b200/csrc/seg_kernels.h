@@ -73,6 +73,18 @@ cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int s
 cudaError_t launch_gate(const GateArgs& a, cudaStream_t st);
 cudaError_t launch_attention_simt(const AttnArgs& a, int B, cudaStream_t st);
 cudaError_t launch_attention_tc(const AttnArgs& a, int B, cudaStream_t st);
+// positional convolution + bias + GELU + residual, in place on the fp32 residual stream (posconv_tc.cu)
+struct PosConvArgs {
+  const __nv_bfloat16* stage; int stage_rows; int stage_ld;   // [B][stage_rows = T + 128][16 x 64] zero-padded 16-bit copy
+  const __nv_bfloat16* w; int ldw; long long w_gstride;        // [16][Dg][128 taps x 64]
+  const float* bias;                                           // [16 x Dg]
+  float* x; int ldx;                                           // [B*T][ldx] residual stream, updated in place
+  int B; int T; int Dg; int fp16;
+};
+struct PosConvPlan;
+PosConvPlan* posconv_plan_create(const PosConvArgs& a);
+void posconv_plan_destroy(PosConvPlan* p);
+cudaError_t posconv_plan_launch(const PosConvPlan* p, cudaStream_t st);
 struct AttnPlan;  // tensor maps + launch geometry of the tcgen05 attention kernel (attention_tc.cu)
 AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B);
 void attention_tc_plan_destroy(AttnPlan* p);
