@@ -432,7 +432,13 @@ static int plan_impl(dz_seg* s, int B, int N) {
       p.step("conv0_moments", [s, B, N, T0, mom](cudaStream_t st) { return launch_conv0_moments(s->cur_wav, B, N, T0, mom, st); });
       p.step("conv0_gn_coef", [=](cudaStream_t st) { return launch_conv0_gn_coef(mom, w0, g0, b0, B, C0, T0, coef, st); });
     }
-    p.step("conv0", [s, c, B, large](cudaStream_t st) { Conv0Args cc = c; cc.wav = s->cur_wav; return launch_conv0(cc, B, large, st); },
+    // conv0_tc.cu (tcgen05 variant) is experimental and opt-in: DZ_CONV0_TC=1
+    static const bool c0_want_tc = [] { const char* e = getenv("DZ_CONV0_TC"); return e && e[0] == '1'; }();
+    const bool c0_tc = c0_want_tc && s->gemm_impl == 0 && conv0_tc_eligible(c);
+    p.step("conv0", [s, c, B, large, c0_tc](cudaStream_t st) {
+             Conv0Args cc = c; cc.wav = s->cur_wav;
+             return c0_tc ? launch_conv0_tc(cc, B, large, st) : launch_conv0(cc, B, large, st);
+           },
            0.0, (double)B * N * 4.0 + (double)B * Tl[0] * Cp[0] * 2.0 * P);
     p.tap_bf("conv0", act[0], (long long)B * Tl[0], a.conv_channels[0], Cp[0]);
   }

@@ -65,6 +65,8 @@ cudaError_t launch_conv0_moments(const float* wav, int B, int N, int T0, double*
 cudaError_t launch_conv0_gn_coef(const double* mom, const float* w, const float* gamma, const float* beta, int B, int C0,
                                  int T0, float* coef, cudaStream_t st);
 cudaError_t launch_conv0(const Conv0Args& a, int B, bool large, cudaStream_t st);
+bool conv0_tc_eligible(const Conv0Args& a);                                         // conv0_tc.cu (tcgen05 variant, fp16 mode)
+cudaError_t launch_conv0_tc(const Conv0Args& a, int B, bool large, cudaStream_t st);
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st);
 cudaError_t launch_axpy_mix(const float* x, float* mix, float w, int init, long long n, cudaStream_t st);
 cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int seq_len, int seq_rows_out, int row_off,
