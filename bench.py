@@ -380,7 +380,7 @@ def run_pipeline_bench(args, world, rank, local, dist):
     d = classes[dom]
     if d["flops"] > 0:
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (" + dom + ")", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel / gemm_tc_kernel / posconv_tc_kernel (" + dom + ")", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor"], "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)",
                 "share_of_network_time": d["ms"] / total_ms}
     else:
@@ -545,7 +545,7 @@ def main():
         npass = 3 if args.precision == "bf16x3" else 1
         if dom in ("gemm", "attention"):
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel" if dom == "gemm" else "attention", "achieved": ach,
+            roof = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel / gemm_tc_kernel / posconv_tc_kernel" if dom == "gemm" else "attention_tc2_kernel", "achieved": ach,
                     "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
                     "peak_source": peaks["src"] + " (sustained bf16)", "launches_per_step": d["n"],
                     "share_of_step": d["ms"] / total_ms, "tensor_passes": npass}
