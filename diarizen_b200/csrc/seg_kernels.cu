@@ -409,7 +409,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
-      v[i] = (c < a.C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = (c < a.C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // rows are padded to ldx >= rup(C, 4)
+      if (c + 3 >= a.C) {   // the chunk that straddles C: the padding columns hold stale data
+        if (c + 1 >= a.C) v[i].y = 0.f;
+        if (c + 2 >= a.C) v[i].z = 0.f;
+        v[i].w = 0.f;
+      }
     }
     float4 m[NV];
     if ((mix_in || mix_out) && !a.mix_init) {
@@ -448,8 +453,14 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
       const int c = (lane + 32 * i) * 4;
       if (c < a.C) {
         const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-        v[i] = make_float4(d0, d1, d2, d3);
+        float4 dd = make_float4(d0, d1, d2, d3);
+        if (c + 3 >= a.C) {
+          if (c + 1 >= a.C) dd.y = 0.f;
+          if (c + 2 >= a.C) dd.z = 0.f;
+          dd.w = 0.f;
+        }
+        q = fmaf(dd.x, dd.x, q); q = fmaf(dd.y, dd.y, q); q = fmaf(dd.z, dd.z, q); q = fmaf(dd.w, dd.w, q);
+        v[i] = dd;
       }
     }
     const float rstd = rsqrtf(warp_sum(q) * invC + 1e-5f);
@@ -462,7 +473,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
                              fmaf(v[i].z * rstd, g4.z, b4.z), fmaf(v[i].w * rstd, g4.w, b4.w));
       if (ACT == 1) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
       if (ACT == 2) { y.x = apply_act(y.x, a.act); y.y = apply_act(y.y, a.act); y.z = apply_act(y.z, a.act); y.w = apply_act(y.w, a.act); }
-      if (c >= a.C) y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 >= a.C) {   // columns >= C (and whole chunks past C) are written as zeros
+        if (c >= a.C) y.x = 0.f;
+        if (c + 1 >= a.C) y.y = 0.f;
+        if (c + 2 >= a.C) y.z = 0.f;
+        y.w = 0.f;
+      }
       v[i] = y;
     }
     if (mix_out) {
@@ -526,7 +542,10 @@ cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
   const long long want = (a.rows + 7) / 8;
   const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   static const bool generic = [] { const char* e = getenv("DZ_LN_GENERIC"); return e && e[0] == '1'; }();
-  const bool fast = !generic && (a.C % 4) == 0 && (a.ldx % 4) == 0 && (a.y_f32 == nullptr || a.ldy % 4 == 0);
+  // rows must be padded to a multiple of 4 floats; with the layer mix (always D-wide, D % 4 == 0) or a ragged C the
+  // chunk straddling C is masked in registers
+  const bool fast = !generic && (a.ldx % 4) == 0 && a.ldx >= ((a.C + 3) & ~3) && (a.y_f32 == nullptr || (a.ldy % 4 == 0 && a.ldy >= ((a.C + 3) & ~3))) &&
+                    (a.mix == nullptr || (a.C % 4) == 0);
   if (fast) {
     if (a.C <= 256) launch_ln_fast_nv<2>(a, grid, st);
     else if (a.C <= 512) launch_ln_fast_nv<4>(a, grid, st);
