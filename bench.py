@@ -172,7 +172,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_reference_pipeline(args):
@@ -212,7 +212,7 @@ def run_reference_pipeline(args):
                       "window_s": dur, "windows_per_step": nw},
            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_name(args):
@@ -427,10 +427,22 @@ def run_pipeline_bench(args, world, rank, local, dist):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "breakdown": breakdown,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_OUT = sys.stdout
+
+
+def emit(obj) -> None:
+    """The ONE JSON line of the contract goes to the real stdout; everything else this process prints (the pipeline's
+    reference-compatible progress prints, warnings) is routed to stderr by main()."""
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    sys.stdout = sys.stderr
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -588,7 +600,7 @@ def main():
             "clocks": clocks,
             "breakdown": breakdown,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
