@@ -1,0 +1,75 @@
+"""Checkpoint averaging for the recipes' stage-4 inference.
+
+reference: diarizen/ckpt_utils.py:16-60 (average_checkpoints / average_states / load_metric_summary) and
+recipes/diar_ssl/infer_avg.py:268-286 (which checkpoints are averaged).  Model-loading-time host code: the averaged
+state dict is what `SegmentationModel` uploads; nothing here runs per recording."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Dict, List, Sequence, Union
+
+import torch
+
+Ckpt = Union[str, Path, Dict]
+
+
+def average_states(states_list: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """Key-wise mean of state dicts (ckpt_utils.py:32-43).  Like the reference, the sum runs in the dtype of the first
+    checkpoint and the final `/ qty` is a true division (integer buffers such as `num_batches_tracked` come out as floats);
+    unlike it the inputs are left untouched."""
+    if len(states_list) == 0:
+        raise ValueError("no checkpoints to average")
+    qty = len(states_list)
+    avg = {k: v.clone() for k, v in states_list[0].items()}
+    for st in states_list[1:]:
+        if st.keys() != avg.keys():
+            raise KeyError("checkpoints to average have different keys")
+        for k in avg:
+            avg[k] += st[k].to(avg[k].device)
+    return {k: v / qty for k, v in avg.items()}
+
+
+def _path_of(ckpt: Ckpt) -> Path:
+    return Path(ckpt["bin_path"]) if isinstance(ckpt, dict) else Path(ckpt)
+
+
+def average_checkpoints(checkpoint_list: Sequence[Ckpt]) -> Dict[str, torch.Tensor]:
+    """ckpt_utils.py:16-30 without the nn.Module round trip: entries are paths or the `{'bin_path': ...}` records that
+    `load_metric_summary` produces."""
+    states = [torch.load(str(_path_of(c)), map_location="cpu") for c in checkpoint_list]
+    return average_states(states)
+
+
+def load_metric_summary(metric_file: Union[str, Path], ckpt_path: Union[str, Path]) -> List[Dict]:
+    """ckpt_utils.py:45-60: one record per validation line of the trainer's summary file."""
+    out = []
+    ckpt_path = Path(ckpt_path)
+    with open(metric_file, "r") as f:
+        for line in f:
+            if not line.strip():
+                continue
+            if "Validation Loss/DER" not in line:
+                raise ValueError(f"unexpected line in metric summary: {line!r}")
+            tok = line.split()
+            epoch = tok[4].split(":")[0]
+            out.append({"epoch": int(epoch), "bin_path": ckpt_path / f"epoch_{str(epoch).zfill(4)}/pytorch_model.bin",
+                        "Loss": float(tok[-3]), "DER": float(tok[-1])})
+    return out
+
+
+def select_checkpoints(val_metric_lst: List[Dict], val_metric: str = "Loss", val_mode: str = "best", avg_ckpt_num: int = 5) -> List[Dict]:
+    """infer_avg.py:270-286: `best` = the n best epochs, `prev` = the best epoch and the n-1 before it, `center` = a window of
+    n epochs centred on the best one."""
+    ranked = sorted(val_metric_lst, key=lambda r: r[val_metric])
+    best = val_metric_lst.index(ranked[0])
+    if val_mode == "best":
+        sel = ranked[:avg_ckpt_num]
+    elif val_mode == "prev":
+        sel = val_metric_lst[best - avg_ckpt_num + 1: best + 1]
+    elif val_mode == "center":
+        sel = val_metric_lst[best - avg_ckpt_num // 2: best + avg_ckpt_num // 2 + 1]
+    else:
+        raise ValueError(f"unknown val_mode {val_mode!r}")
+    if len(sel) != avg_ckpt_num:
+        raise AssertionError(f"selected {len(sel)} checkpoints, wanted {avg_ckpt_num}")
+    return sel

@@ -81,7 +81,8 @@ def _load_toml(path: Path) -> dict:
 class DiariZenPipeline:
     def __init__(self, diarizen_hub, embedding_model, config_parse: Optional[Dict[str, Any]] = None,
                  rttm_out_dir: Optional[str] = None, *, precision: str = "fp16", device=None,
-                 _seg: Optional[SegmentationModel] = None, _emb: Optional[EmbeddingModel] = None, _config: Optional[dict] = None):
+                 _seg: Optional[SegmentationModel] = None, _emb: Optional[EmbeddingModel] = None, _config: Optional[dict] = None,
+                 segmentation: Optional[list] = None):
         if _config is None:
             diarizen_hub = Path(diarizen_hub)
             config = _load_toml(diarizen_hub / "config.toml")
@@ -126,7 +127,14 @@ class DiariZenPipeline:
         if _seg is None:
             margs = config["model"]["args"]
             src = margs.get("wavlm_src", "wavlm_base")
-            sd = torch.load(str(diarizen_hub / "pytorch_model.bin"), map_location="cpu")
+            if segmentation:
+                # checkpoint-averaged inference (recipes/*/infer_avg.py:292-303, ckpt_utils.py:16-43): a list of
+                # checkpoint paths / {'bin_path': ...} records is averaged key-wise at load time
+                from .checkpoints import average_checkpoints
+                sd = average_checkpoints(segmentation) if len(segmentation) > 1 else torch.load(
+                    str(segmentation[0]["bin_path"] if isinstance(segmentation[0], dict) else segmentation[0]), map_location="cpu")
+            else:
+                sd = torch.load(str(diarizen_hub / "pytorch_model.bin"), map_location="cpu")
             if os.path.isfile(src):
                 ck = torch.load(src, map_location="cpu")
                 arch = arch_from_reference_config(ck["config"], name=Path(src).stem)
