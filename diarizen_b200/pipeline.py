@@ -44,22 +44,31 @@ def _closest_frame(t: float) -> int:
     return int(np.rint((t - 0.5 * FRAME_DURATION) / FRAME_STEP))
 
 
+def _to_16k(w: torch.Tensor, sr: int) -> torch.Tensor:
+    """Other sample rates go through the same resampler the reference uses (pyannote `Audio` -> torchaudio.functional.resample,
+    pa/core/io.py:187-221); decode-time preprocessing on the host, before the recording is uploaded."""
+    if sr == SR:
+        return w
+    try:
+        import torchaudio.functional as AF
+    except Exception as e:   # pragma: no cover
+        raise ValueError(f"input is {sr} Hz and torchaudio is not available to resample it to {SR} Hz") from e
+    return AF.resample(w[None], sr, SR)[0].contiguous()
+
+
 def load_waveform(in_wav) -> torch.Tensor:
     """-> mono (N,) float32 in [-1, 1], 16 kHz.  Stands in for `torchaudio.load(in_wav)[0][0]` (inference.py:127-128)."""
     if isinstance(in_wav, dict):
         w = in_wav["waveform"] if "waveform" in in_wav else None
         if w is None:
             return load_waveform(in_wav["audio"])
-        if int(in_wav.get("sample_rate", SR)) != SR:
-            raise ValueError("only 16 kHz input is supported")
         w = torch.as_tensor(w, dtype=torch.float32)
-        return w[0] if w.dim() == 2 else w
+        w = w[0] if w.dim() == 2 else w
+        return _to_16k(w, int(in_wav.get("sample_rate", SR)))
     if isinstance(in_wav, (str, os.PathLike, io.BytesIO)):
         with wave.open(in_wav if isinstance(in_wav, io.BytesIO) else str(in_wav), "rb") as f:
             sr, nch, sw, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
             raw = f.readframes(n)
-        if sr != SR:
-            raise ValueError(f"only 16 kHz input is supported (got {sr} Hz); resample first")
         if sw == 2:
             x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
         elif sw == 4:
@@ -68,7 +77,7 @@ def load_waveform(in_wav) -> torch.Tensor:
             x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
         else:
             raise ValueError(f"unsupported sample width {sw}")
-        return torch.from_numpy(x.reshape(-1, nch)[:, 0].copy())   # force channel 0 (inference.py:128)
+        return _to_16k(torch.from_numpy(x.reshape(-1, nch)[:, 0].copy()), sr)   # force channel 0 (inference.py:128)
     raise TypeError(f"input must be either a str, BytesIO or a ProtocolFile; there was {type(in_wav)}")
 
 

@@ -117,3 +117,29 @@ def test_window_sharding_gloo_world2():
         p.join(timeout=60)
     expect = np.repeat(np.arange(1, 12, dtype=np.uint8)[:, None], 7, axis=1)
     assert np.array_equal(outs[0], expect) and np.array_equal(outs[1], expect)
+
+
+def test_load_waveform_resamples_other_rates(tmp_path):
+    """(f3) non-16 kHz input goes through torchaudio's resampler like the reference's Audio class."""
+    import wave
+    import numpy as np
+    import torch
+    torchaudio = __import__("pytest").importorskip("torchaudio")
+    from diarizen_b200.pipeline import load_waveform
+    sr = 8000
+    t = np.arange(sr) / sr
+    x = (0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    stereo = np.stack([x, -x], axis=1)
+    p = tmp_path / "a8k.wav"
+    with wave.open(str(p), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(sr)
+        f.writeframes((stereo * 32767).astype("<i2").tobytes())
+    w = load_waveform(str(p))
+    assert w.shape == (16000,) and w.dtype == torch.float32
+    ref = torchaudio.functional.resample(torch.from_numpy((x * 32767).astype("<i2").astype(np.float32) / 32768.0)[None], sr, 16000)[0]
+    assert torch.equal(w, ref)
+    # channel 0, 440 Hz preserved
+    spec = torch.fft.rfft(w).abs()
+    assert int(spec.argmax()) == 440
+    w2 = load_waveform({"waveform": torch.from_numpy(x)[None], "sample_rate": sr})
+    assert w2.shape == (16000,)
