@@ -201,14 +201,20 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_kernel(const Conv0Arg
         sc = rsqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * invC + 1e-5f);
         of = -mean * sc;
       }
-      if (t < a.T0) {
-        bf16* orow = a.out + (long long)b * a.out_bstride + (long long)t * ldo;
+      {
+        // tcgen05.ld is warp-collective (.sync.aligned): every lane takes part in the loads, also the lanes whose frame lies
+        // past the end of the window (the last tile of a window has 127 valid rows); only the stores are predicated
+        const bool rvalid = t < a.T0;
+        bf16* orow = a.out + (long long)b * a.out_bstride + (long long)(rvalid ? t : 0) * ldo;
         for (int j = 0; j < nj; ++j) {
           const int c0 = col_lo + 32 * j;
           uint32_t r[32];
           if (c0 < NP) {
             tmem_ld_32x32(tmem_base + lane_off + (uint32_t)c0, r);
             tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r[c] = 0u;
           }
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_kernel(const Conv0Arg
               y1 = (c + 1 < C0) ? gelu_erf(fmaf(y1, g.z, g.w)) : 0.f;
               w4[e] = pack2_16<1>(y0, y1);
             }
-            *reinterpret_cast<uint4*>(orow + cb) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            if (rvalid) *reinterpret_cast<uint4*>(orow + cb) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
       }

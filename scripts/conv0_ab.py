@@ -29,7 +29,7 @@ for simt in ("1", "0"):
     f = f"/tmp/conv0_{simt}.pt"
     env = dict(os.environ, DZ_CONV0_TC="0" if simt == "1" else "1")
     try:
-        r = subprocess.run([sys.executable, __file__, name, B, N, "child", f], env=env, timeout=90, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, __file__, name, B, N, "child", f], env=env, timeout=25, capture_output=True, text=True)
         print(r.stdout[-600:], r.stderr[-600:], flush=True)
         if r.returncode == 0:
             outs[simt] = torch.load(f)
