@@ -6,6 +6,7 @@
 // reference: diarizen/pipelines/inference.py:131-132, pyannote-audio/pyannote/audio/core/inference.py:543-666,
 //   pipelines/utils/diarization.py:122-157,193-239, pipelines/speaker_diarization.py:271-320,377-425,
 //   pipelines/clustering.py:159-173,404-418 (scipy linkage(method="centroid") on unit-norm embeddings).
+#include <cstdlib>
 #include <string>
 
 #include "../../include/diarizen_b200.h"
@@ -285,6 +286,102 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(double* __restri
   }
 }
 
+// v2 of the merge loop (opt-in, DZ_LINKAGE_V2=1, until it has been checked bit-for-bit against scipy on hardware): the same
+// arithmetic and tie-breaking, but (a) size / nn / nnd / todo live in shared memory instead of L2, (b) the nearest neighbour
+// of the merged cluster y is the block-argmin of the distances the update loop has just computed, so row y is not re-read,
+// (c) the remaining rescans keep four loads in flight per lane.
+__global__ void __launch_bounds__(1024) linkage_centroid_kernel_v2(double* __restrict__ Dm, int N, double* __restrict__ Z,
+                                                                   int* __restrict__ cid) {
+  extern __shared__ double lsm[];
+  double* nnd = lsm;                                   // [N]
+  int* nn = reinterpret_cast<int*>(nnd + N);           // [N]
+  int* size = nn + N;                                  // [N]
+  int* todo = size + N;                                // [N]
+  __shared__ ArgMin sc[32];
+  __shared__ int s_ntodo;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  for (int i = tid; i < N; i += nt) { size[i] = 1; cid[i] = i; }
+  __syncthreads();
+  for (int i = tid >> 5; i < N; i += nt >> 5) {
+    ArgMin best{INFINITY, 0x7fffffff};
+    const double* row = Dm + (long long)i * N;
+    for (int j = lane; j < N; j += 32)
+      if (j != i) best = amin(best, ArgMin{row[j], j});
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, best.v, o); t.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+      best = amin(best, t);
+    }
+    if (lane == 0) { nn[i] = best.i; nnd[i] = best.v; }
+  }
+  __syncthreads();
+  for (int step = 0; step < N - 1; ++step) {
+    ArgMin best{INFINITY, 0x7fffffff};
+    for (int i = tid; i < N; i += nt)
+      if (size[i] > 0) best = amin(best, ArgMin{nnd[i], i});
+    best = block_argmin(best, sc);
+    int x = best.i, y = nn[x];
+    if (x > y) { const int t = x; x = y; y = t; }
+    const double dxy = Dm[(long long)x * N + y];
+    const int nx = size[x], ny = size[y];
+    __syncthreads();
+    if (tid == 0) {
+      const int ix = cid[x], iy = cid[y];
+      Z[step * 4 + 0] = (double)min(ix, iy);
+      Z[step * 4 + 1] = (double)max(ix, iy);
+      Z[step * 4 + 2] = dxy;
+      Z[step * 4 + 3] = (double)(nx + ny);
+      s_ntodo = 0;
+    }
+    __syncthreads();
+    const double nxy = (double)(nx + ny);
+    const double cxy = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dxy), dxy), nxy);
+    ArgMin ybest{INFINITY, 0x7fffffff};
+    for (int z = tid; z < N; z += nt) {
+      if (size[z] == 0 || z == x || z == y) continue;
+      const double dxz = Dm[(long long)x * N + z], dyz = Dm[(long long)y * N + z];
+      const double t1 = __dmul_rn(__dmul_rn((double)nx, dxz), dxz);
+      const double t2 = __dmul_rn(__dmul_rn((double)ny, dyz), dyz);
+      const double nd = __dsqrt_rn(__ddiv_rn(__dsub_rn(__dadd_rn(t1, t2), cxy), nxy));
+      Dm[(long long)y * N + z] = nd;
+      Dm[(long long)z * N + y] = nd;
+      ybest = amin(ybest, ArgMin{nd, z});
+      const int nz = nn[z];
+      if (nz == x || nz == y) {
+        todo[atomicAdd(&s_ntodo, 1)] = z;
+      } else if (nd < nnd[z]) {
+        nn[z] = y; nnd[z] = nd;
+      }
+    }
+    ybest = block_argmin(ybest, sc);   // = the rescan of row y in v1: min over live z of (d(y,z), z), lowest z on ties
+    if (tid == 0) { size[x] = 0; size[y] = nx + ny; cid[y] = N + step; nn[y] = ybest.i; nnd[y] = ybest.v; }
+    __syncthreads();
+    const int ntodo = s_ntodo;
+    for (int q = tid >> 5; q < ntodo; q += nt >> 5) {
+      const int i = todo[q];
+      ArgMin b2{INFINITY, 0x7fffffff};
+      const double* row = Dm + (long long)i * N;
+      for (int j0 = lane; j0 < N; j0 += 128) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u; v[u] = (j < N) ? row[j] : INFINITY; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < N && j != i && size[j] > 0) b2 = amin(b2, ArgMin{v[u], j});
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, b2.v, o); t.i = __shfl_xor_sync(0xffffffffu, b2.i, o);
+        b2 = amin(b2, t);
+      }
+      if (lane == 0) { nn[i] = b2.i; nnd[i] = b2.v; }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Constrained assignment (one distinct cluster per local speaker, maximise the summed score): exhaustive search over
 // the S! / (S - min(S,K))! ... injective maps, S <= 4, K <= 32.  One thread per chunk.
@@ -381,6 +478,19 @@ int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_
   int* cid = (int*)w; w += (size_t)N * 4;
   int* nn = (int*)w; w += (size_t)N * 4;
   int* todo = (int*)w;
+  static const bool v2 = [] { const char* e = getenv("DZ_LINKAGE_V2"); return e && e[0] == '1'; }();
+  const size_t smem = (size_t)N * (8 + 3 * 4);
+  if (v2 && smem <= 200 * 1024) {
+    static size_t attr = 0;
+    if (smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(linkage_centroid_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(DZ_ERR_CUDA, cudaGetErrorString(e));
+      attr = smem;
+    }
+    linkage_centroid_kernel_v2<<<1, 1024, smem, (cudaStream_t)stream>>>(dist_dev, N, z_dev, cid);
+    CK_LAUNCH();
+    return DZ_OK;
+  }
   linkage_centroid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist_dev, N, z_dev, size, cid, nn, nnd, todo);
   CK_LAUNCH();
   return DZ_OK;
