@@ -51,7 +51,7 @@ DZ_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if ((++n & 0x3Fu) == 0) {
-      if (clock64() - t0 > 1000000000LL) {   // ~0.5 s: three orders of magnitude above any legitimate wait on this path
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s: three orders of magnitude above any legitimate wait on this path
         printf("dz: mbarrier timeout block(%d,%d,%d) thread %d barrier@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
                threadIdx.x, smem_u32(bar), parity);
         __trap();
