@@ -30,38 +30,38 @@ def load_scp(scp_file) -> Dict[str, str]:
 
 
 def build_parser() -> argparse.ArgumentParser:
-    p = argparse.ArgumentParser("This script performs diarization using the DiariZen pipeline (diarizen_b200)", add_help=True,
+    p = argparse.ArgumentParser("diarizen_b200: diarize every recording of a wav.scp and write one RTTM per session", add_help=True,
                                 usage="%(prog)s [options]")
-    p.add_argument("-i", "--in_wav_scp", type=str, required=True, help="test wav.scp.", dest="in_wav_scp")
-    p.add_argument("--diarizen_hub", type=str, default=None, help="Path to DiariZen model hub directory.")
-    p.add_argument("--embedding_model", type=str, required=True, help="Path to pretrained embedding model.")
+    p.add_argument("-i", "--in_wav_scp", type=str, required=True, help="list of recordings, one `<session> <path>` per line", dest="in_wav_scp")
+    p.add_argument("--diarizen_hub", type=str, default=None, help="model directory (config.toml, pytorch_model.bin, plda/)")
+    p.add_argument("--embedding_model", type=str, required=True, help="WeSpeaker ResNet34 checkpoint")
     # experiment mode (infer_avg.py)
-    p.add_argument("-C", "--configuration", type=str, default=None, help="Configuration (*.toml) of a training run.")
-    p.add_argument("-o", "--out_dir", type=str, default=None, help="Path to output directory (experiment mode).")
-    p.add_argument("--avg_ckpt_num", type=int, default=5, help="the number of checkpoints of model averaging")
-    p.add_argument("--val_metric", type=str, default="Loss", choices=["Loss", "DER"], help="validation metric")
-    p.add_argument("--val_mode", type=str, default="best", choices=["best", "prev", "center"], help="validation metric mode")
-    p.add_argument("--val_metric_summary", type=str, default="", help="val_metric_summary")
-    p.add_argument("--segmentation_model", type=str, default="", help="Path to pretrained segmentation model.")
+    p.add_argument("-C", "--configuration", type=str, default=None, help="config.toml of a training run (switches to experiment mode)")
+    p.add_argument("-o", "--out_dir", type=str, default=None, help="where the RTTMs go in experiment mode")
+    p.add_argument("--avg_ckpt_num", type=int, default=5, help="how many checkpoints are averaged")
+    p.add_argument("--val_metric", type=str, default="Loss", choices=["Loss", "DER"], help="column of the metric summary used to rank epochs")
+    p.add_argument("--val_mode", type=str, default="best", choices=["best", "prev", "center"], help="best: the n best epochs; prev: the best and the n-1 before it; center: a window around the best")
+    p.add_argument("--val_metric_summary", type=str, default="", help="per-epoch validation summary written by the trainer")
+    p.add_argument("--segmentation_model", type=str, default="", help="single segmentation checkpoint (experiment mode without averaging)")
     # inference parameters
-    p.add_argument("--seg_duration", type=int, default=16, help="Segment duration in seconds.")
-    p.add_argument("--segmentation_step", type=float, default=0.1, help="Shifting ratio during segmentation")
-    p.add_argument("--batch_size", type=int, default=32, help="Input batch size for inference.")
+    p.add_argument("--seg_duration", type=int, default=16, help="window length in seconds")
+    p.add_argument("--segmentation_step", type=float, default=0.1, help="window hop as a fraction of the window length")
+    p.add_argument("--batch_size", type=int, default=32, help="windows per batch in the configuration (results do not depend on it)")
     p.add_argument("--apply_median_filtering", action=argparse.BooleanOptionalAction, default=True,
-                   help="Apply median filtering to segmentation output.")
+                   help="11-frame median filter on the window decisions")
     # clustering parameters
     p.add_argument("--clustering_method", type=str, default="VBxClustering", choices=["VBxClustering", "AgglomerativeClustering"],
-                   help="Clustering method to use.")
-    p.add_argument("--min_speakers", type=int, default=1, help="Minimum number of speakers.")
-    p.add_argument("--max_speakers", type=int, default=20, help="Maximum number of speakers.")
-    p.add_argument("--ahc_criterion", type=str, default="distance", help="AHC criterion (for VBx).")
-    p.add_argument("--ahc_threshold", type=float, default=0.6, help="AHC threshold.")
-    p.add_argument("--min_cluster_size", type=int, default=13, help="Minimum cluster size (for AHC).")
-    p.add_argument("--Fa", type=float, default=0.07, help="VBx Fa parameter.")
-    p.add_argument("--Fb", type=float, default=0.8, help="VBx Fb parameter.")
-    p.add_argument("--lda_dim", type=int, default=128, help="VBx LDA dimension.")
-    p.add_argument("--max_iters", type=int, default=20, help="VBx maximum iterations.")
-    p.add_argument("--rttm_out_dir", type=str, default=None, required=False, help="Path to output folder (hub mode).")
+                   help="global clustering of the window-level speakers")
+    p.add_argument("--min_speakers", type=int, default=1, help="lower bound on the number of speakers")
+    p.add_argument("--max_speakers", type=int, default=20, help="upper bound on the number of speakers")
+    p.add_argument("--ahc_criterion", type=str, default="distance", help="flat-cluster criterion of the AHC initialisation (VBx)")
+    p.add_argument("--ahc_threshold", type=float, default=0.6, help="linkage threshold (distance) or cluster count (maxclust)")
+    p.add_argument("--min_cluster_size", type=int, default=13, help="smaller AHC clusters are merged into their nearest large one")
+    p.add_argument("--Fa", type=float, default=0.07, help="VBx: scale of the sufficient statistics")
+    p.add_argument("--Fb", type=float, default=0.8, help="VBx: speaker regularisation")
+    p.add_argument("--lda_dim", type=int, default=128, help="VBx: dimensions kept after the PLDA transform")
+    p.add_argument("--max_iters", type=int, default=20, help="VBx: iteration cap")
+    p.add_argument("--rttm_out_dir", type=str, default=None, required=False, help="where the RTTMs go in hub mode")
     p.add_argument("--precision", type=str, default="fp16", choices=["fp16", "bf16", "bf16x3"], help="operand precision mode")
     return p
 
