@@ -367,6 +367,12 @@ def run_pipeline_bench(args, world, rank, local, dist):
     pipe._embedding.embed_windows(wb[:ebs], torch.ones(ebs, 4, T, device="cuda"))
     emb_prof = pipe._embedding.profile()
     n_seg_b, n_emb_b = Cn / bsz, Cn / ebs
+    if args.profile_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        with open(args.profile_out, "w") as f:
+            json.dump({"seg": [{"name": n, "ms": m, "flops": fl, "bytes": by} for n, m, fl, by in seg_prof],
+                       "emb": [{"name": n, "ms": m, "flops": fl} for n, m, fl in emb_prof],
+                       "seg_batches": n_seg_b, "emb_batches": n_emb_b}, f, indent=0)
     classes = {}
     for name, pms, fl, by in seg_prof:
         c = classes.setdefault("seg:" + classify(name), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})

@@ -34,6 +34,8 @@ class Annotation:
 
     def __setitem__(self, key, label):
         segment, track = key
+        if not (segment.end - segment.start) > 1e-6:    # empty segments are not kept (a turn made of the last frame only)
+            return
         self._tracks.append((segment, track, label))
 
     def __len__(self) -> int:
@@ -43,10 +45,11 @@ class Annotation:
         return sorted({l for _, _, l in self._tracks})
 
     def itertracks(self, yield_label: bool = False) -> Iterator:
-        for seg, trk, lab in sorted(self._tracks, key=lambda x: (x[0].start, x[0].end)):
+        # segments in (start, end) order; tracks sharing a segment in the order of their names
+        for seg, trk, lab in sorted(self._tracks, key=lambda x: (x[0].start, x[0].end, str(x[1]), str(x[2]))):
             yield (seg, trk, lab) if yield_label else (seg, trk)
 
     def to_rttm(self) -> str:
-        uri = self.uri if self.uri is not None else "<NA>"
+        uri = self.uri if self.uri else "<NA>"
         return "".join(f"SPEAKER {uri} 1 {s.start:.3f} {s.duration:.3f} <NA> <NA> {lab} <NA> <NA>\n"
                        for s, _, lab in self.itertracks(yield_label=True))

@@ -337,7 +337,12 @@ class DiariZenPipeline:
         a region starts at the middle of the first active frame and ends at the middle of the first inactive one."""
         F, K = discrete.shape
         ann = Annotation(uri=uri)
-        mid = lambda i: i * FRAME_STEP + 0.5 * FRAME_DURATION
+
+        def mid(i):
+            # middle of frame i = half the sum of its two ends: this order of operations decides the third decimal of
+            # the RTTM times (pinned by tests/golden/glue_*.npz, produced by the reference's Binarize)
+            s = i * FRAME_STEP
+            return 0.5 * (s + (s + FRAME_DURATION))
         for k in range(K):
             y = discrete[:, k].astype(np.int8)
             if F == 0:

@@ -36,7 +36,10 @@ class SlidingWindow:
         return int(np.rint((t - self.start - 0.5 * self.duration) / self.step))
 
     def middle(self, i: int) -> float:
-        return self.start + i * self.step + 0.5 * self.duration
+        # pyannote.core: window[i] = Segment(start + i * step, start + i * step + duration); Segment.middle = .5 * (start + end).
+        # The order of operations matters for the third decimal printed in the RTTM (pinned by tests/golden/glue_*.npz).
+        s = self.start + i * self.step
+        return 0.5 * (s + (s + self.duration))
 
 
 def slide_windows(wav: np.ndarray, window: int, step: int) -> np.ndarray:
@@ -211,11 +214,11 @@ def assign_embeddings(embeddings: np.ndarray, ci, si, train_clusters: np.ndarray
 
 
 def cluster_call(embeddings: np.ndarray, binarized: np.ndarray, threshold: float, min_cluster_size: int,
-                 min_clusters: Optional[int], max_clusters: Optional[int], **hooks):
+                 min_clusters: Optional[int], max_clusters: Optional[int], num_clusters: Optional[int] = None, **hooks):
     """clustering.py:247-322."""
     train, ci, si = filter_embeddings(embeddings, binarized)
     n = train.shape[0]
-    num_clusters, min_c, max_c = set_num_clusters(n, None, min_clusters, max_clusters)
+    num_clusters, min_c, max_c = set_num_clusters(n, num_clusters, min_clusters, max_clusters)
     if max_c < 2:
         C, S, _ = embeddings.shape
         return np.zeros((C, S), dtype=np.int8), np.ones((C, S, 1)), np.mean(train, axis=0, keepdims=True)
@@ -278,7 +281,9 @@ def to_rttm(turns: List[Tuple[float, float, int]], uri: Optional[str]) -> str:
     """pyannote.core Annotation.to_rttm: tracks sorted by (start, end), then insertion."""
     u = uri if uri is not None else "<NA>"
     lines = []
-    for s, e, k in sorted(turns, key=lambda x: (x[0], x[1])):
+    for s, e, k in sorted(turns, key=lambda x: (x[0], x[1], str(x[2]))):
+        if not (e - s) > 1e-6:       # pyannote.core drops empty segments (Segment.__bool__, precision 1e-6)
+            continue
         lines.append(f"SPEAKER {u} 1 {s:.3f} {e - s:.3f} <NA> <NA> {k} <NA> <NA>\n")
     return "".join(lines)
 
@@ -301,7 +306,10 @@ def run_pipeline(wav: np.ndarray, seg_fn, emb_fn, chunk_duration: float, step_ra
     masks = embedding_masks(seg, min_num_frames)
     emb_chunks = crop_chunks(wav, C, chunk_duration, chunk_step)
     emb = np.asarray(emb_fn(emb_chunks, masks), dtype=np.float32)
-    hard, _, centroids = cluster_call(emb, seg, threshold, min_cluster_size, min_speakers, max_speakers, **hooks)
+    if hooks.get("cluster_fn") is not None:      # e.g. the VBx variant (oracle/vbx_oracle.py)
+        hard, _, centroids = hooks["cluster_fn"](emb, seg)
+    else:
+        hard, _, centroids = cluster_call(emb, seg, threshold, min_cluster_size, min_speakers, max_speakers, **hooks)
     count = np.minimum(count, max_speakers).astype(np.int8)
     hard = hard.copy()
     hard[np.sum(seg, axis=1) == 0] = -2
