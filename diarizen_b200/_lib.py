@@ -170,6 +170,7 @@ def lib() -> C.CDLL:
         "dz_pdist": [vp, i32, i32, vp, vp],
         "dz_linkage_centroid": [vp, i32, vp, vp, vp],
         "dz_assign": [vp, i32, i32, i32, vp, vp],
+        "dz_dendrogram_cut": [vp, i32, C.c_double, i32, i32, i32, i32, i32, vp, vp, vp, vp],
         "dz_vbx_model": [vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp],
         "dz_vbx_resp": [vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp, vp],
     }.items():
@@ -177,6 +178,8 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = args
     L.dz_linkage_workspace_bytes.restype = i64
     L.dz_linkage_workspace_bytes.argtypes = [i32]
+    L.dz_dendrogram_cut_workspace_bytes.restype = i64
+    L.dz_dendrogram_cut_workspace_bytes.argtypes = [i32]
     _lib = L
     return L
 
@@ -195,5 +198,5 @@ EXPORTS = [
     "dz_emb_create", "dz_emb_destroy", "dz_emb_set_param", "dz_emb_finalize", "dz_emb_num_fbank_frames", "dz_emb_forward",
     "dz_emb_last_launches", "dz_emb_tap_fbank", "dz_emb_num_steps", "dz_emb_profile",
     "dz_median_filter", "dz_speaker_count", "dz_embedding_masks", "dz_reconstruct", "dz_pdist", "dz_linkage_workspace_bytes",
-    "dz_linkage_centroid", "dz_assign", "dz_vbx_model", "dz_vbx_resp",
+    "dz_linkage_centroid", "dz_dendrogram_cut_workspace_bytes", "dz_dendrogram_cut", "dz_assign", "dz_vbx_model", "dz_vbx_resp",
 ]

@@ -126,7 +126,9 @@ def fcluster_maxclust(Z: np.ndarray, max_nc: int) -> np.ndarray:
             stack.pop()
         return False
 
-    lo, hi = 0, n - 1
+    if max_nc >= n:                      # the installed scipy (1.18) answers singletons outright
+        return np.arange(1, n + 1, dtype=np.int32)
+    lo, hi = -1, n - 1                   # the bisection may end on merge 0 (n - 1 flat clusters)
     while hi - lo > 1:
         i = (lo + hi) >> 1
         if exceeds(md[i]):
@@ -146,20 +148,50 @@ def _cosine_cdist(A: np.ndarray, B: np.ndarray) -> np.ndarray:
         return 1.0 - (A @ B.T) / (na[:, None] * nb[None, :])
 
 
+class DeviceDendrogram:
+    """Centroid-linkage dendrogram of unit-norm embeddings, built and kept on the GPU: float64 distance matrix (dz_pdist),
+    merge loop (dz_linkage_centroid, bit-identical to scipy.cluster.hierarchy.linkage(method="centroid")), and the
+    flat-cluster selection (dz_dendrogram_cut).  Only the N labels and eight counters come back to the host."""
+
+    def __init__(self, unit_embeddings: np.ndarray, device=None):
+        L = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda")
+        x = torch.as_tensor(np.ascontiguousarray(unit_embeddings, dtype=np.float32), device=self.device)
+        self.n, D = x.shape
+        N = self.n
+        dist = torch.empty((N, N), dtype=torch.float64, device=self.device)
+        self._Z = torch.empty((N - 1, 4), dtype=torch.float64, device=self.device)
+        ws = torch.empty(int(L.dz_linkage_workspace_bytes(N)), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.dz_pdist(C.c_void_p(x.data_ptr()), N, D, C.c_void_p(dist.data_ptr()), st))
+            _lib.check(L.dz_linkage_centroid(C.c_void_p(dist.data_ptr()), N, C.c_void_p(self._Z.data_ptr()), C.c_void_p(ws.data_ptr()), st))
+
+    def Z(self) -> np.ndarray:
+        """scipy-layout linkage matrix (N-1, 4) float64 on the host."""
+        return self._Z.cpu().numpy()
+
+    def cut(self, threshold: float, min_cluster_size: int = 1, min_clusters: int = 1, max_clusters: Optional[int] = None,
+            num_clusters: Optional[int] = None, force_iteration: int = -1):
+        """-> (labels (N,) int32 in scipy's fcluster numbering minus one, info dict)."""
+        L = _lib.lib()
+        N = self.n
+        labels = torch.empty(N, dtype=torch.int32, device=self.device)
+        info = torch.zeros(8, dtype=torch.int32, device=self.device)
+        ws = torch.empty(int(L.dz_dendrogram_cut_workspace_bytes(N)), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.dz_dendrogram_cut(C.c_void_p(self._Z.data_ptr()), N, float(threshold), int(min_cluster_size), int(min_clusters),
+                                           int(max_clusters if max_clusters is not None else N), int(num_clusters or 0), int(force_iteration),
+                                           C.c_void_p(labels.data_ptr()), C.c_void_p(info.data_ptr()), C.c_void_p(ws.data_ptr()), st))
+        i = info.cpu().numpy()
+        return labels.cpu().numpy(), {"num_large": int(i[0]), "iteration": int(i[1]), "found_only": bool(i[2]), "num_flat": int(i[3]),
+                                      "num_large_at_threshold": int(i[4]), "target": int(i[5])}
+
+
 def device_linkage_centroid(unit_embeddings: np.ndarray, device=None) -> np.ndarray:
     """scipy linkage(method="centroid", metric="euclidean") on the GPU -> Z (N-1, 4) float64."""
-    L = _lib.lib()
-    dev = torch.device(device if device is not None else "cuda")
-    x = torch.as_tensor(np.ascontiguousarray(unit_embeddings, dtype=np.float32), device=dev)
-    N, D = x.shape
-    dist = torch.empty((N, N), dtype=torch.float64, device=dev)
-    Z = torch.empty((N - 1, 4), dtype=torch.float64, device=dev)
-    ws = torch.empty(int(L.dz_linkage_workspace_bytes(N)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(L.dz_pdist(C.c_void_p(x.data_ptr()), N, D, C.c_void_p(dist.data_ptr()), st))
-        _lib.check(L.dz_linkage_centroid(C.c_void_p(dist.data_ptr()), N, C.c_void_p(Z.data_ptr()), C.c_void_p(ws.data_ptr()), st))
-    return Z.cpu().numpy()
+    return DeviceDendrogram(unit_embeddings, device).Z()
 
 
 def device_assign(soft: np.ndarray, device=None) -> np.ndarray:
@@ -175,9 +207,36 @@ def device_assign(soft: np.ndarray, device=None) -> np.ndarray:
     return hard.cpu().numpy()
 
 
+def frame_statistics(segmentations) -> Tuple[np.ndarray, np.ndarray, int]:
+    """(C,T,S) {0,1} -> per (chunk, speaker): active frames, frames where it is the only active speaker; T."""
+    seg = np.asarray(getattr(segmentations, "data", segmentations))
+    alone = seg * (seg.sum(axis=2, keepdims=True) == 1)
+    return seg.sum(axis=1), alone.sum(axis=1), seg.shape[1]
+
+
+def absorb_small_clusters(unit_embeddings: np.ndarray, labels: np.ndarray, min_size: int) -> np.ndarray:
+    """Every flat cluster with fewer than `min_size` members joins the large cluster whose centroid is nearest in cosine
+    distance; the survivors are renumbered 0..K-1 in increasing order of their old number (clustering.py:494-513).
+    With no small cluster the labels are returned untouched (their scipy numbering then reaches the RTTM)."""
+    counts = np.bincount(labels)
+    ids = np.flatnonzero(counts)
+    big, small = ids[counts[ids] >= min_size], ids[counts[ids] < min_size]
+    if big.size == 0:
+        return np.zeros_like(labels)
+    if small.size == 0:
+        return labels
+    mean_of = lambda k: np.mean(unit_embeddings[labels == k], axis=0)
+    nearest = np.argmin(_cosine_cdist(np.stack([mean_of(k) for k in big]), np.stack([mean_of(k) for k in small])), axis=0)
+    remap = np.full(counts.size, -1, dtype=np.int64)
+    remap[big] = np.arange(big.size)            # big is sorted: rank == position
+    remap[small] = remap[big[nearest]]
+    return remap[labels]
+
+
 class AgglomerativeClustering:
     """reference: clustering.py:325-513 (only method="centroid" with metric="cosine" is what DiariZen configures:
-    diarizen/pipelines/inference.py:64-71)."""
+    diarizen/pipelines/inference.py:64-71).  Same call convention and hyper-parameter attributes; the dendrogram, the
+    choice of the cut and the assignment run on the GPU."""
 
     def __init__(self, metric: str = "cosine", max_num_embeddings: float = np.inf, constrained_assignment: bool = True,
                  device=None):
@@ -189,125 +248,67 @@ class AgglomerativeClustering:
         self.min_cluster_size = 30
         self.device = device
 
-    # -- clustering.py:88-109
     @staticmethod
     def set_num_clusters(num_embeddings, num_clusters=None, min_clusters=None, max_clusters=None):
-        min_clusters = num_clusters or min_clusters or 1
-        min_clusters = max(1, min(num_embeddings, min_clusters))
-        max_clusters = num_clusters or max_clusters or num_embeddings
-        max_clusters = max(1, min(num_embeddings, max_clusters))
-        if min_clusters > max_clusters:
-            raise ValueError(
-                f"min_clusters must be smaller than (or equal to) max_clusters "
-                f"(here: min_clusters={min_clusters:g} and max_clusters={max_clusters:g}).")
-        if min_clusters == max_clusters:
-            num_clusters = min_clusters
-        return num_clusters, min_clusters, max_clusters
+        """Clamp the requested cluster-count range to [1, num_embeddings]; a fixed `num_clusters` collapses the range."""
+        lo = min(num_embeddings, num_clusters or min_clusters or 1)
+        hi = min(num_embeddings, num_clusters or max_clusters or num_embeddings)
+        lo, hi = max(1, lo), max(1, hi)
+        if lo > hi:
+            raise ValueError(f"min_clusters must be smaller than (or equal to) max_clusters (here: min_clusters={lo:g} and max_clusters={hi:g}).")
+        return (lo if lo == hi else num_clusters), lo, hi
 
-    # -- clustering.py:111-157; `active_frames` / `single_frames` are (C,S) counts (device kernel dz_embedding_masks)
     def filter_embeddings(self, embeddings: np.ndarray, active_frames: np.ndarray, single_frames: np.ndarray,
                           num_frames: int, min_frames_ratio: float = 0.1):
-        active = active_frames > 0
-        valid = ~np.any(np.isnan(embeddings), axis=2)
-        min_frames = round(min_frames_ratio * num_frames)
-        ci, si = np.where(active * valid * (single_frames >= min_frames))
-        if len(ci) < 2:
-            ci, si = np.where(active * valid * (single_frames >= 0))
+        """Embeddings used to build the clusters: active speakers with a finite embedding and at least
+        round(ratio * T) single-speaker frames (all active ones when fewer than two qualify).  `active_frames` /
+        `single_frames` are the (C,S) counters of dz_embedding_masks."""
+        ok = (active_frames > 0) & ~np.isnan(embeddings).any(axis=2)
+        keep = ok & (single_frames >= round(min_frames_ratio * num_frames))
+        if np.count_nonzero(keep) < 2:
+            keep = ok
+        ci, si = np.nonzero(keep)
         return embeddings[ci, si], ci, si
 
-    # -- clustering.py:363-513
     def cluster(self, embeddings: np.ndarray, min_clusters: int, max_clusters: int, num_clusters: Optional[int] = None):
+        """(N,D) training embeddings -> (N,) cluster indices."""
         if self.method != "centroid" or self.metric != "cosine":
             raise ValueError("only method='centroid' with metric='cosine' is implemented (the DiariZen configuration)")
         n = embeddings.shape[0]
-        mcs = min(self.min_cluster_size, max(1, round(0.1 * n)))
         if n == 1:
             return np.zeros((1,), dtype=np.uint8)
-        emb = embeddings.copy()
+        min_size = min(self.min_cluster_size, max(1, round(0.1 * n)))
         with np.errstate(divide="ignore", invalid="ignore"):
-            emb /= np.linalg.norm(emb, axis=-1, keepdims=True)
-        import os as _os, time as _time
-        _t0 = _time.perf_counter()
-        Z = device_linkage_centroid(emb, self.device)
-        _t1 = _time.perf_counter()
-        clusters = fcluster_distance(Z, self.threshold) - 1
-        if _os.environ.get("DZ_TIMING") is not None:
-            print(f"[dz timing] linkage N={n}: device pdist+linkage {(_t1 - _t0) * 1e3:.1f} ms, fcluster {(_time.perf_counter() - _t1) * 1e3:.1f} ms")
-        uniq, counts = np.unique(clusters, return_counts=True)
-        large = uniq[counts >= mcs]
-        nlarge = len(large)
-        if nlarge < min_clusters:
-            num_clusters = min_clusters
-        elif nlarge > max_clusters:
-            num_clusters = max_clusters
-        if num_clusters is not None and nlarge != num_clusters:
-            _Z = np.copy(Z)
-            _Z[:, 2] = np.arange(n - 1)
-            best_it, best_n = n - 1, 1
-            for it in np.argsort(np.abs(Z[:, 2] - self.threshold)):
-                if _Z[it, 3] < mcs:
-                    continue
-                clusters = fcluster_distance(_Z, it) - 1
-                uniq, counts = np.unique(clusters, return_counts=True)
-                large = uniq[counts >= mcs]
-                nlarge = len(large)
-                if abs(nlarge - num_clusters) < abs(best_n - num_clusters):
-                    best_it, best_n = it, nlarge
-                if nlarge == num_clusters:
-                    break
-            if best_n != num_clusters:
-                clusters = fcluster_distance(_Z, best_it) - 1
-                uniq, counts = np.unique(clusters, return_counts=True)
-                large = uniq[counts >= mcs]
-                nlarge = len(large)
-                print(f"Found only {nlarge} clusters. Using a smaller value than {mcs} for `min_cluster_size` might help.")
-        if nlarge == 0:
-            clusters[:] = 0
-            return clusters
-        small = uniq[counts < mcs]
-        if len(small) == 0:
-            return clusters
-        lc = np.vstack([np.mean(emb[clusters == k], axis=0) for k in large])
-        scn = np.vstack([np.mean(emb[clusters == k], axis=0) for k in small])
-        d = _cosine_cdist(lc, scn)
-        for sk, lk in enumerate(np.argmin(d, axis=0)):
-            clusters[clusters == small[sk]] = large[lk]
-        _, clusters = np.unique(clusters, return_inverse=True)
-        return clusters
+            unit = embeddings / np.linalg.norm(embeddings, axis=-1, keepdims=True)
+        labels, info = DeviceDendrogram(unit, self.device).cut(self.threshold, min_size, min_clusters, max_clusters, num_clusters)
+        if info["found_only"]:
+            print(f"Found only {info['num_large']} clusters. Using a smaller value than {min_size} for `min_cluster_size` might help.")
+        self.last_cut = info
+        return absorb_small_clusters(unit, labels.astype(np.int64), min_size)
 
-    # -- clustering.py:175-245
     def assign_embeddings(self, embeddings, ci, si, train_clusters):
+        """Centroids = plain means of the raw training embeddings per cluster; soft score = 2 - cosine distance of every
+        (chunk, speaker) embedding to every centroid; hard = one distinct cluster per local speaker, maximal total score."""
         K = int(np.max(train_clusters)) + 1
         Cn, S, D = embeddings.shape
         train = embeddings[ci, si]
-        centroids = np.vstack([np.mean(train[train_clusters == k], axis=0) for k in range(K)])
+        centroids = np.stack([train[train_clusters == k].mean(axis=0) for k in range(K)])
         soft = 2 - _cosine_cdist(embeddings.reshape(Cn * S, D), centroids).reshape(Cn, S, K)
         if self.constrained_assignment:
-            sc = np.nan_to_num(soft, nan=np.nanmin(soft))
-            hard = device_assign(sc, self.device)
+            hard = device_assign(np.nan_to_num(soft, nan=np.nanmin(soft)), self.device)
         else:
             hard = np.argmax(soft, axis=2).astype(np.int8)
         return hard, soft, centroids
 
-    # -- clustering.py:247-322
     def __call__(self, embeddings: np.ndarray, segmentations=None, num_clusters=None, min_clusters=None,
-                 max_clusters=None, frame_stats: Optional[Tuple[np.ndarray, np.ndarray]] = None, **kwargs):
-        if frame_stats is None:
-            seg = np.asarray(getattr(segmentations, "data", segmentations))
-            active_frames = np.sum(seg, axis=1)
-            single = (np.sum(seg, axis=2, keepdims=True) == 1)
-            single_frames = np.sum(seg * single, axis=1)
-            T = seg.shape[1]
-        else:
-            active_frames, single_frames, T = frame_stats
+                 max_clusters=None, frame_stats: Optional[Tuple[np.ndarray, np.ndarray, int]] = None, **kwargs):
+        active_frames, single_frames, T = frame_stats if frame_stats is not None else frame_statistics(segmentations)
         train, ci, si = self.filter_embeddings(embeddings, active_frames, single_frames, T)
-        n = train.shape[0]
-        num_clusters, min_c, max_c = self.set_num_clusters(n, num_clusters, min_clusters, max_clusters)
-        if max_c < 2:
+        num_clusters, lo, hi = self.set_num_clusters(train.shape[0], num_clusters, min_clusters, max_clusters)
+        if hi < 2:      # a single speaker is imposed: nothing to cluster
             Cn, S, _ = embeddings.shape
             return (np.zeros((Cn, S), dtype=np.int8), np.ones((Cn, S, 1)), np.mean(train, axis=0, keepdims=True))
-        tc = self.cluster(train, min_c, max_c, num_clusters)
-        return self.assign_embeddings(embeddings, ci, si, tc)
+        return self.assign_embeddings(embeddings, ci, si, self.cluster(train, lo, hi, num_clusters))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -410,24 +411,17 @@ class VBxClustering(AgglomerativeClustering):
 
     def __call__(self, embeddings: np.ndarray, segmentations=None, num_clusters=None, min_clusters=None,
                  max_clusters=None, frame_stats: Optional[Tuple[np.ndarray, np.ndarray]] = None, **kwargs):
-        if frame_stats is None:
-            seg = np.asarray(getattr(segmentations, "data", segmentations))
-            active_frames = np.sum(seg, axis=1)
-            single = (np.sum(seg, axis=2, keepdims=True) == 1)
-            single_frames = np.sum(seg * single, axis=1)
-            T = seg.shape[1]
-        else:
-            active_frames, single_frames, T = frame_stats
+        active_frames, single_frames, T = frame_stats if frame_stats is not None else frame_statistics(segmentations)
         train, _, _ = self.filter_embeddings(embeddings, active_frames, single_frames, T, min_frames_ratio=0.1)
         Cn, S, D = embeddings.shape
         if train.shape[0] < 2:
             return (np.zeros((Cn, S), dtype=np.int8), np.ones((Cn, S, 1)), np.mean(train, axis=0, keepdims=True))
         normed = train / np.linalg.norm(train, axis=1, keepdims=True)
-        Z = device_linkage_centroid(normed, self.device)
+        dendrogram = DeviceDendrogram(normed, self.device)
         if self.ahc_criterion == "distance":
-            ahc = fcluster_distance(Z, self.ahc_threshold) - 1
+            ahc, _ = dendrogram.cut(self.ahc_threshold)
         elif self.ahc_criterion == "maxclust":
-            ahc = fcluster_maxclust(Z, int(self.ahc_threshold)) - 1
+            ahc = fcluster_maxclust(dendrogram.Z(), int(self.ahc_threshold)) - 1
         else:
             raise ValueError(f"unsupported ahc_criterion {self.ahc_criterion!r}")
         _, ahc = np.unique(ahc, return_inverse=True)

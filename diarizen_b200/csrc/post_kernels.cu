@@ -138,6 +138,45 @@ __global__ void reconstruct_kernel(const uint8_t* __restrict__ seg, const int8_t
   }
 }
 
+// Same for 32 < K <= 128 clusters (int8 labels allow 127): the per-frame activations live in shared memory ([k][thread],
+// conflict-free) instead of registers.  One thread per frame.
+__global__ void __launch_bounds__(128) reconstruct_wide_kernel(const uint8_t* __restrict__ seg, const int8_t* __restrict__ hard,
+                                                               const int* __restrict__ start, const uint8_t* __restrict__ count, int C,
+                                                               int T, int S, int K, int Kout, int F, uint8_t* __restrict__ discrete,
+                                                               float* __restrict__ act_out) {
+  extern __shared__ float wact[];   // [Kout][128]
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float* act = wact + threadIdx.x;
+  for (int k = 0; k < Kout; ++k) act[k * 128] = 0.f;
+  if (f >= F) return;
+  int lo = 0, hi = C;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (start[mid] + T > f) hi = mid; else lo = mid + 1; }
+  for (int c = lo; c < C && start[c] <= f; ++c) {
+    const uint8_t* p = seg + ((long long)c * T + (f - start[c])) * S;
+    for (int s = 0; s < S; ++s) {
+      const int k = hard[c * S + s];
+      if (k < 0 || k >= K || !p[s]) continue;
+      bool dup = false;                       // max over the local speakers of one cluster, not their sum
+      for (int q = 0; q < s; ++q) dup |= (hard[c * S + q] == k) && p[q];
+      if (!dup) act[k * 128] += 1.f;
+    }
+  }
+  if (act_out)
+    for (int k = 0; k < Kout; ++k) act_out[(long long)f * Kout + k] = act[k * 128];
+  for (int k = 0; k < Kout; ++k) discrete[(long long)f * Kout + k] = 0;
+  const int cnt = min((int)count[f], Kout);
+  for (int i = 0; i < cnt; ++i) {
+    int best = -1; float bv = -1.f;
+    for (int k = 0; k < Kout; ++k) {
+      const float v = act[k * 128];
+      if (v > bv) { bv = v; best = k; }       // chosen entries are marked -2 below
+    }
+    if (best < 0) break;
+    discrete[(long long)f * Kout + best] = 1;
+    act[best * 128] = -2.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Euclidean distance matrix in float64, exactly as scipy.spatial.distance.pdist computes it on the float64 copy of the
 // (float32, unit-norm) embeddings: d = sqrt(sum_k (u_k - v_k)^2) accumulated sequentially, no fused multiply-add.
@@ -424,6 +463,56 @@ __global__ void assign_kernel(const double* __restrict__ soft, int C, int S, int
   for (int s = 0; s < S; ++s) hard[c * S + s] = (int8_t)best[s];
 }
 
+// K >= S: every local speaker gets a cluster, and some optimal map gives each speaker one of its S best clusters (at
+// most S - 1 of them can be taken by the others), so the search runs over S candidates per speaker (<= 256 maps) whatever K.
+// Candidates are ranked by (score descending, cluster index ascending); among equal totals the lexicographically smallest
+// map wins, as in assign_kernel.
+__global__ void assign_topk_kernel(const double* __restrict__ soft, int C, int S, int K, int8_t* __restrict__ hard) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* sc = soft + (long long)c * S * K;
+  int cand[4][4];
+  double cval[4][4];
+  for (int s = 0; s < S; ++s) {
+    for (int j = 0; j < S; ++j) {
+      int bk = -1; double bv = -INFINITY;
+      for (int k = 0; k < K; ++k) {
+        bool taken = false;
+        for (int q = 0; q < j; ++q) taken |= cand[s][q] == k;
+        if (taken) continue;
+        const double v = sc[s * K + k];
+        if (bk < 0 || v > bv) { bv = v; bk = k; }
+      }
+      cand[s][j] = bk; cval[s][j] = bv;
+    }
+  }
+  int best[4] = {-2, -2, -2, -2};
+  double bestv = -INFINITY;
+  int total = 1;
+  for (int s = 0; s < S; ++s) total *= S;
+  for (int code = 0; code < total; ++code) {
+    int a[4] = {-1, -1, -1, -1};
+    int t = code;
+    double v = 0.0;
+    bool ok = true;
+    for (int s = 0; s < S && ok; ++s) {
+      const int j = t % S; t /= S;
+      a[s] = cand[s][j];
+      for (int q = 0; q < s; ++q) ok &= a[q] != a[s];
+      v += cval[s][j];
+    }
+    if (!ok) continue;
+    bool better = v > bestv;
+    if (!better && v == bestv) {
+      for (int s = 0; s < S; ++s) {
+        if (a[s] != best[s]) { better = a[s] < best[s]; break; }
+      }
+    }
+    if (better) { bestv = v; for (int s = 0; s < S; ++s) best[s] = a[s]; }
+  }
+  for (int s = 0; s < S; ++s) hard[c * S + s] = (int8_t)best[s];
+}
+
 }  // namespace dz
 
 using namespace dz;
@@ -452,9 +541,20 @@ int dz_embedding_masks(const uint8_t* seg_dev, int C, int T, int S, int min_fram
 }
 int dz_reconstruct(const uint8_t* seg_dev, const int8_t* hard_dev, const int32_t* start_dev, const uint8_t* count_dev, int C, int T,
                    int S, int K, int Kout, int F, uint8_t* discrete_dev, float* act_dev, void* stream) {
-  if (!seg_dev || !hard_dev || !start_dev || !count_dev || !discrete_dev || K > 32 || K < 1 || Kout < K || Kout > 32)
-    return fail(DZ_ERR_INVALID, "bad argument (1 <= K <= Kout <= 32)");
-  reconstruct_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, Kout, F, discrete_dev, act_dev);
+  if (!seg_dev || !hard_dev || !start_dev || !count_dev || !discrete_dev || K > 128 || K < 1 || Kout < K || Kout > 255 || S < 1 || S > 8)
+    return fail(DZ_ERR_INVALID, "bad argument (1 <= K <= 128, K <= Kout <= 255)");
+  if (Kout <= 32) {
+    reconstruct_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, Kout, F, discrete_dev, act_dev);
+  } else {
+    const size_t smem = (size_t)Kout * 128 * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(reconstruct_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(DZ_ERR_CUDA, cudaGetErrorString(e));
+      attr = smem;
+    }
+    reconstruct_wide_kernel<<<(F + 127) / 128, 128, smem, (cudaStream_t)stream>>>(seg_dev, hard_dev, start_dev, count_dev, C, T, S, K, Kout, F, discrete_dev, act_dev);
+  }
   CK_LAUNCH();
   return DZ_OK;
 }
@@ -478,7 +578,7 @@ int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_
   int* cid = (int*)w; w += (size_t)N * 4;
   int* nn = (int*)w; w += (size_t)N * 4;
   int* todo = (int*)w;
-  static const bool v2 = [] { const char* e = getenv("DZ_LINKAGE_V2"); return e && e[0] == '1'; }();
+  static const bool v2 = [] { const char* e = getenv("DZ_LINKAGE_V1"); return !(e && e[0] == '1'); }();
   const size_t smem = (size_t)N * (8 + 3 * 4);
   if (v2 && smem <= 200 * 1024) {
     static size_t attr = 0;
@@ -496,8 +596,9 @@ int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_
   return DZ_OK;
 }
 int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream) {
-  if (!soft_dev || !hard_dev || S < 1 || S > 4 || K < 1 || K > 31) return fail(DZ_ERR_INVALID, "bad argument (S <= 4, K <= 31)");
-  assign_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
+  if (!soft_dev || !hard_dev || S < 1 || S > 4 || K < 1 || K > 127) return fail(DZ_ERR_INVALID, "bad argument (S <= 4, K <= 127: labels are int8)");
+  if (K < S || K <= 4) assign_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
+  else assign_topk_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
   CK_LAUNCH();
   return DZ_OK;
 }

@@ -432,8 +432,9 @@ static int plan_impl(dz_seg* s, int B, int N) {
       p.step("conv0_moments", [s, B, N, T0, mom](cudaStream_t st) { return launch_conv0_moments(s->cur_wav, B, N, T0, mom, st); });
       p.step("conv0_gn_coef", [=](cudaStream_t st) { return launch_conv0_gn_coef(mom, w0, g0, b0, B, C0, T0, coef, st); });
     }
-    // conv0_tc.cu (tcgen05 variant) is opt-in (DZ_CONV0_TC=1) until it has been validated and timed on the s80 configurations
-    static const bool c0_want_tc = [] { const char* e = getenv("DZ_CONV0_TC"); return e && e[0] == '1'; }();
+    // conv0_tc.cu (tcgen05) is the default since it matched the oracle on the s80 configurations at the benchmarked sizes
+    // (tests/test_bench_config_gpu.py); DZ_CONV0_SIMT=1 selects the CUDA-core kernel for A/B runs
+    static const bool c0_want_tc = [] { const char* e = getenv("DZ_CONV0_SIMT"); return !(e && e[0] == '1'); }();
     const bool c0_tc = c0_want_tc && s->gemm_impl == 0 && conv0_tc_eligible(c);
     p.step("conv0", [s, c, B, large, c0_tc](cudaStream_t st) {
              Conv0Args cc = c; cc.wav = s->cur_wav;

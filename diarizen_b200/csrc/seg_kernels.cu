@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
 
 cudaError_t launch_glu_dwconv(const DwArgs& a, int B, cudaStream_t st) {
   if (a.ksize > 32) return cudaErrorInvalidValue;
-  static const bool v2 = [] { const char* e = getenv("DZ_DWCONV_V2"); return e && e[0] == '1'; }();
+  static const bool v2 = [] { const char* e = getenv("DZ_DWCONV_V1"); return !(e && e[0] == '1'); }();
   if (v2) {
     const size_t smem2 = sizeof(float) * (size_t)(DW2_TT + a.ksize - 1) * a.A;
     if (smem2 <= 200 * 1024) {

@@ -31,7 +31,7 @@ from .archs import SegArch, arch_from_reference_config, get_arch, init_state_dic
 from .clustering import AgglomerativeClustering, VBxClustering
 from .embedding import EmbeddingModel
 from .segmentation import SegmentationModel
-from .sharding import gather_windows, window_range
+from .sharding import gather_records, window_range
 
 SR = 16000
 FRAME_DURATION = 400 / SR    # receptive field of the conv stack (model_wavlm_conformer.py:126-176)
@@ -161,6 +161,8 @@ class DiariZenPipeline:
         self.rttm_out_dir = rttm_out_dir
         self._L = _lib.lib()
         self.last = {}
+        self.collect_timing = os.environ.get("DZ_TIMING") is not None
+        self._timing, self._t_last = {}, None
 
     # ------------------------------------------------------------------------------------------------
     @classmethod
@@ -215,121 +217,203 @@ class DiariZenPipeline:
         has_last = (num_samples < window) or ((num_samples - window) % step > 0)
         return window, step, n_full + int(has_last)
 
-    def diarize_waveform(self, wav: torch.Tensor, shard: Optional[bool] = None) -> Dict[str, Any]:
-        """wav (N,) fp32 -> dict with every intermediate the parity tests compare.
-
-        shard: window-shard this recording over the ranks of the initialised torch.distributed group (one all-gather,
-        result on rank 0 only).  Default: shard when a process group exists.  Policy for many recordings:
-        give whole recordings to ranks (`shard=False`, no collective) and window-shard only when there are fewer
-        recordings than ranks."""
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        if shard is False:
-            dist = None
-        rank = dist.get_rank() if dist else 0
-        world = dist.get_world_size() if dist else 1
-        dev = self.device
-        L = self._L
-        Nw = wav.shape[0]
-        import time as _time
-        timing = {}
-        _tm = os.environ.get("DZ_TIMING") is not None
-
-        def _mark(name, _t=[None]):
-            if not _tm:
-                return
-            torch.cuda.synchronize()
-            now = _time.perf_counter()
-            if _t[0] is not None:
-                timing[name] = timing.get(name, 0.0) + (now - _t[0])
-            _t[0] = now
-        _mark("start")
-        window, step, Cn = self._windows(Nw)
-        chunk_step_s = self.segmentation_step * self.seg_duration
-        T = self._segmentation.num_frames(window)
-        S = 4
-        pad_to = (Cn - 1) * step + window
-        wdev = torch.zeros(max(pad_to, Nw), device=dev, dtype=torch.float32)
-        wdev[:Nw] = wav.to(dev, torch.float32)
+    # ------------------------------------------------------------------------------------------------
+    # stage 1 - every rank, on its own window range: the two networks and the per-window kernels between them
+    # ------------------------------------------------------------------------------------------------
+    def _front(self, wdev: torch.Tensor, Cn: int, window: int, step: int, T: int, c0: int, c1: int, per: int):
+        """-> (seg (per,T,S) uint8 median-filtered, stats (per,S,2) int32, emb (per,S,256) fp32); rows >= c1-c0 are padding."""
+        dev, L, S = self.device, self._L, 4
+        st = vp(torch.cuda.current_stream(dev).cuda_stream)
         chunks = wdev.as_strided((Cn, window), (step, 1))
-        # window range of this rank
-        c0, c1, per = window_range(Cn, rank, world)
-        seg_local = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
+        n_loc = c1 - c0
+        raw = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
         bs = self.engine_windows
-        # The engines plan (workspace + tensor maps) per batch shape: the ragged last batch is padded to the full
-        # batch size instead of triggering a re-plan (two multi-GB reallocations per recording otherwise).
-        seg_tail = None
+        # The engines plan (workspace + tensor maps) per batch shape: the ragged last batch is padded to the full batch
+        # size instead of triggering a re-plan (two multi-GB reallocations per recording otherwise).
         for a in range(c0, c1, bs):
             b = min(a + bs, c1)
-            if b - a == bs or (c1 - c0) < bs:
-                self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=seg_local[a - c0:b - c0])
+            if b - a == bs or n_loc < bs:
+                self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=raw[a - c0:b - c0])
             else:
                 wpad = torch.zeros((bs, window), device=dev, dtype=torch.float32)
                 wpad[:b - a] = chunks[a:b]
-                seg_tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
-                self._segmentation.hard(wpad, want_logp=False, ml_out=seg_tail)
-                seg_local[a - c0:b - c0] = seg_tail[:b - a]
-        seg = gather_windows(seg_local, Cn, world).contiguous()
-        _mark("segmentation")
-        st = vp(torch.cuda.current_stream().cuda_stream)
+                tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
+                self._segmentation.hard(wpad, want_logp=False, ml_out=tail)
+                raw[a - c0:b - c0] = tail[:b - a]
+        self._mark("segmentation")
+        return (raw,) + self._masks_and_embeddings(raw, wdev, chunks, window, step, T, c0, c1, per)
+
+    def _masks_and_embeddings(self, raw, wdev, chunks, window, step, T, c0, c1, per):
+        dev, L, S = self.device, self._L, 4
+        st = vp(torch.cuda.current_stream(dev).cuda_stream)
         if self.apply_median_filtering:
-            filt = torch.empty_like(seg)
-            _lib.check(L.dz_median_filter(vp(seg.data_ptr()), vp(filt.data_ptr()), Cn, T, S, 11, st))
-            seg = filt
-        # speaker counting
+            seg = torch.empty_like(raw)
+            _lib.check(L.dz_median_filter(vp(raw.data_ptr()), vp(seg.data_ptr()), per, T, S, 11, st))
+        else:
+            seg = raw
+        min_num_frames = math.ceil(T * self._embedding.min_num_samples / (self.seg_duration * SR))
+        masks = torch.empty((per, S, T), device=dev, dtype=torch.float32)
+        stats = torch.empty((per, S, 2), device=dev, dtype=torch.int32)
+        _lib.check(L.dz_embedding_masks(vp(seg.data_ptr()), per, T, S, min_num_frames, vp(masks.data_ptr()), vp(stats.data_ptr()), st))
+        # chunk crops as the reference computes them (io.py:359-364): start = floor(c * step_s * sr) in float64
+        chunk_step_s = self.segmentation_step * self.seg_duration
+        e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(c0, c1)]
+        same = all(e == c * step for e, c in zip(e_starts, range(c0, c1)))
+        self._mark("count_masks")
+        emb = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
+        ebs = self.engine_emb_windows
+        n_loc = c1 - c0
+        for a in range(c0, c1, ebs):
+            b = min(a + ebs, c1)
+            if same:
+                wv = chunks[a:b].contiguous()
+            else:
+                wv = torch.stack([wdev[e_starts[c - c0]:e_starts[c - c0] + window] for c in range(a, b)])
+            mk = masks[a - c0:b - c0]
+            if b - a < ebs and n_loc >= ebs:   # pad the ragged last batch (see above)
+                wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
+                mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
+            emb[a - c0:b - c0] = self._embedding.embed_windows(wv, mk)[:b - a]
+        self._mark("embedding")
+        return seg, stats, emb
+
+    # ------------------------------------------------------------------------------------------------
+    # stage 2 - one rank: counting, clustering, reconstruction
+    # ------------------------------------------------------------------------------------------------
+    def _back(self, seg: torch.Tensor, stats: torch.Tensor, emb: torch.Tensor, Cn: int, T: int) -> Dict[str, Any]:
+        dev, L, S = self.device, self._L, 4
+        st = vp(torch.cuda.current_stream(dev).cuda_stream)
+        chunk_step_s = self.segmentation_step * self.seg_duration
         starts = np.array([_closest_frame(c * chunk_step_s + 0.5 * FRAME_DURATION) for c in range(Cn)], dtype=np.int32)
         F = _closest_frame(self.seg_duration + (Cn - 1) * chunk_step_s + 0.5 * FRAME_DURATION) + 1
         dstart = torch.as_tensor(starts, device=dev)
         count = torch.empty(F, device=dev, dtype=torch.uint8)
         maxc = int(self.max_speakers) if self.max_speakers else 255
         _lib.check(L.dz_speaker_count(vp(seg.data_ptr()), vp(dstart.data_ptr()), Cn, T, S, F, maxc, vp(count.data_ptr()), st))
-        # embedding masks
-        min_num_frames = math.ceil(T * self._embedding.min_num_samples / (self.seg_duration * SR))
-        masks = torch.empty((Cn, S, T), device=dev, dtype=torch.float32)
-        stats = torch.empty((Cn, S, 2), device=dev, dtype=torch.int32)
-        _lib.check(L.dz_embedding_masks(vp(seg.data_ptr()), Cn, T, S, min_num_frames, vp(masks.data_ptr()), vp(stats.data_ptr()), st))
-        # embeddings (chunk crops as the reference computes them: io.py:359-364)
-        e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(Cn)]
-        same = all(e_starts[c] == c * step for c in range(Cn))
-        _mark("count_masks")
-        emb_local = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
-        ebs = self.engine_emb_windows
-        for a in range(c0, c1, ebs):
-            b = min(a + ebs, c1)
-            if same:
-                wv = chunks[a:b].contiguous()
-            else:
-                wv = torch.stack([wdev[e_starts[c]:e_starts[c] + window] for c in range(a, b)])
-            mk = masks[a:b]
-            if b - a < ebs and (c1 - c0) >= ebs:   # pad the ragged last batch (see above)
-                wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
-                mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
-            emb_local[a - c0:b - c0] = self._embedding.embed_windows(wv, mk)[:b - a]
-        emb = gather_windows(emb_local, Cn, world)          # the single data-path collective (NCCL all-gather)
-        _mark("embedding")
-        if rank != 0:
-            return {}
+        cmax = count.max()                                   # stays on the device until the clustering is done
         emb_np = emb.cpu().numpy()
         stats_np = stats.cpu().numpy()
+        self._mark("gather_to_host")
         hard, _, centroids = self.clustering(embeddings=emb_np, segmentations=None, min_clusters=self.min_speakers,
                                              max_clusters=self.max_speakers,
                                              frame_stats=(stats_np[..., 0], stats_np[..., 1], T))
-        _mark("clustering")
+        self._mark("clustering")
+        if hard.size and int(hard.max()) > 127:
+            raise ValueError(f"{int(hard.max()) + 1} clusters: cluster labels are int8 in the reference (at most 128 clusters)")
         hard = np.array(hard, dtype=np.int8, copy=True)
         hard[stats_np[..., 0] == 0] = -2                                   # inactive speakers (inference.py:166-170)
-        K = int(hard.max()) + 1 if hard.size and hard.max() >= 0 else 1
-        maxspf = int(count.max().item())
+        K = max(int(hard.max()) + 1 if hard.size else 1, 1)
+        Kout = max(K, int(cmax.item()))   # activations are zero padded up to the largest count (diarization.py:222-226)
         dh = torch.as_tensor(hard, device=dev)
-        Kk = max(K, 1)
-        Kout = max(Kk, maxspf)   # activations are zero padded up to the largest count (diarization.py:222-226)
         disc = torch.empty((F, Kout), device=dev, dtype=torch.uint8)
         _lib.check(L.dz_reconstruct(vp(seg.data_ptr()), vp(dh.data_ptr()), vp(dstart.data_ptr()), vp(count.data_ptr()), Cn, T, S,
-                                    Kk, Kout, F, vp(disc.data_ptr()), None, st))
+                                    K, Kout, F, vp(disc.data_ptr()), None, st))
         discrete = disc.cpu().numpy()
-        _mark("reconstruct")
+        self._mark("reconstruct")
         out = {"segmentations": seg, "count": count, "embeddings": emb_np, "hard_clusters": hard, "discrete": discrete,
-               "centroids": centroids, "num_chunks": Cn, "num_frames": T, "timing": timing}
+               "centroids": centroids, "num_chunks": Cn, "num_frames": T, "timing": dict(self._timing)}
         self.last = out
         return out
+
+    def _mark(self, name: Optional[str]):
+        """stage timer (only with `collect_timing`, which synchronises the device at every stage boundary)"""
+        if not self.collect_timing:
+            return
+        import time
+        torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        if name is not None and self._t_last is not None:
+            self._timing[name] = self._timing.get(name, 0.0) + 1e3 * (now - self._t_last)
+        self._t_last = now
+
+    def diarize_waveform(self, wav: torch.Tensor, shard: Optional[bool] = None, root: int = 0) -> Dict[str, Any]:
+        """wav (N,) fp32 -> dict with every intermediate the parity tests compare.
+
+        shard: window-shard this recording over the ranks of the initialised torch.distributed group: every rank runs both
+        networks on its window range, ONE all-gather collects the packed per-window records (binarised segmentations,
+        frame counters, embeddings) and rank `root` clusters and reconstructs (result there only, {} elsewhere).  Default:
+        shard when a process group exists.  Policy for many recordings: `diarize_many`."""
+        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        if shard is False:
+            dist = None
+        rank = dist.get_rank() if dist else 0
+        world = dist.get_world_size() if dist else 1
+        dev = self.device
+        self._timing, self._t_last = {}, None
+        with torch.cuda.device(dev):
+            self._mark(None)
+            Nw = wav.shape[0]
+            window, step, Cn = self._windows(Nw)
+            T = self._segmentation.num_frames(window)
+            pad_to = (Cn - 1) * step + window
+            if wav.device == dev and wav.dtype == torch.float32 and Nw >= pad_to:
+                wdev = wav
+            else:
+                wdev = torch.zeros(max(pad_to, Nw), device=dev, dtype=torch.float32)
+                wdev[:Nw] = wav.to(dev, torch.float32, non_blocking=True)
+            c0, c1, per = window_range(Cn, rank, world)
+            _, seg, stats, emb = self._front(wdev, Cn, window, step, T, c0, c1, per)
+            if world > 1:
+                seg, stats, emb = gather_records(seg, stats, emb, Cn, world)
+                self._mark("all_gather")
+                if rank != root:
+                    return {}
+            else:
+                seg, stats, emb = seg[:Cn], stats[:Cn], emb[:Cn]
+            return self._back(seg, stats, emb, Cn, T)
+
+    def diarize_segmentations(self, raw_segmentations, embeddings) -> Dict[str, Any]:
+        """Stage 2 alone: (C,T,4) {0,1} window decisions as they leave the segmentation network and (C,4,256) embeddings ->
+        the same dict as `diarize_waveform` (median filter, counting, clustering, reconstruction).  This is the seam the
+        glue parity tests drive with reference-produced stage inputs."""
+        dev, L, S = self.device, self._L, 4
+        self._timing, self._t_last = {}, None
+        with torch.cuda.device(dev):
+            raw = torch.as_tensor(np.ascontiguousarray(raw_segmentations, dtype=np.uint8), device=dev)
+            Cn, T, _ = raw.shape
+            st = vp(torch.cuda.current_stream(dev).cuda_stream)
+            seg = raw
+            if self.apply_median_filtering:
+                seg = torch.empty_like(raw)
+                _lib.check(L.dz_median_filter(vp(raw.data_ptr()), vp(seg.data_ptr()), Cn, T, S, 11, st))
+            masks = torch.empty((Cn, S, T), device=dev, dtype=torch.float32)
+            stats = torch.empty((Cn, S, 2), device=dev, dtype=torch.int32)
+            _lib.check(L.dz_embedding_masks(vp(seg.data_ptr()), Cn, T, S, 2, vp(masks.data_ptr()), vp(stats.data_ptr()), st))
+            emb = torch.as_tensor(np.ascontiguousarray(embeddings, dtype=np.float32), device=dev)
+            return self._back(seg, stats, emb, Cn, T)
+
+    def diarize_many(self, waveforms, sess_names=None):
+        """Several recordings over the ranks of the process group (BASELINE.json configs[4]).  Whole
+        recordings go to ranks round-robin - no data-path collective, and the rank that owns a recording also clusters it,
+        so the clustering of different recordings runs on different ranks at the same time.  The n mod world recordings left
+        over are window-sharded over all ranks (one all-gather each) with the clustering rank rotating.
+        -> list aligned with `waveforms`: the Annotation on the rank that finished the recording, None elsewhere."""
+        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        rank = dist.get_rank() if dist else 0
+        world = dist.get_world_size() if dist else 1
+        n = len(waveforms)
+        names = list(sess_names) if sess_names is not None else [None] * n
+        whole = (n // world) * world          # recordings handed out whole
+        out = [None] * n
+        for i in range(n):
+            if i < whole:
+                if i % world != rank:
+                    continue
+                res = self.diarize_waveform(load_waveform(waveforms[i]) if not torch.is_tensor(waveforms[i]) else waveforms[i], shard=False)
+            else:
+                res = self.diarize_waveform(load_waveform(waveforms[i]) if not torch.is_tensor(waveforms[i]) else waveforms[i], shard=True,
+                                            root=i % world)
+            if res:
+                out[i] = self._finish(res, names[i])
+        return out
+
+    def _finish(self, res, sess_name):
+        result = self.to_annotation(res["discrete"], sess_name)
+        if self.rttm_out_dir is not None:
+            assert sess_name is not None
+            with open(os.path.join(self.rttm_out_dir, sess_name + ".rttm"), "w") as f:
+                f.write(result.to_rttm())
+        return result
 
     @staticmethod
     def to_annotation(discrete: np.ndarray, uri: Optional[str]) -> Annotation:
@@ -364,9 +448,4 @@ class DiariZenPipeline:
         res = self.diarize_waveform(wav, shard=shard)
         if not res:
             return None
-        result = self.to_annotation(res["discrete"], sess_name)
-        if self.rttm_out_dir is not None:
-            assert sess_name is not None
-            with open(os.path.join(self.rttm_out_dir, sess_name + ".rttm"), "w") as f:
-                f.write(result.to_rttm())
-        return result
+        return self._finish(res, sess_name)

@@ -21,3 +21,41 @@ def gather_windows(local: torch.Tensor, num_windows: int, world: int) -> torch.T
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous())
     return out[:num_windows]
+
+
+def pack_records(seg: torch.Tensor, stats: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
+    """(per,T,S) uint8 + (per,S,2) int32 + (per,S,D) fp32 -> (per, record_bytes) uint8, 4-byte aligned fields."""
+    per = seg.shape[0]
+    nseg = seg[0].numel()
+    o1 = (nseg + 3) // 4 * 4
+    o2 = o1 + stats[0].numel() * 4
+    rec = o2 + emb[0].numel() * 4
+    buf = torch.zeros((per, rec), dtype=torch.uint8, device=seg.device)
+    buf[:, :nseg] = seg.reshape(per, nseg)
+    buf[:, o1:o2] = stats.contiguous().view(torch.uint8).reshape(per, -1)
+    buf[:, o2:] = emb.contiguous().view(torch.uint8).reshape(per, -1)
+    return buf
+
+
+def unpack_records(buf: torch.Tensor, seg_shape, stats_shape, emb_shape):
+    """inverse of pack_records for `buf` (n, record_bytes); shapes are per-window shapes."""
+    n = buf.shape[0]
+    nseg = 1
+    for d in seg_shape:
+        nseg *= d
+    nst = 1
+    for d in stats_shape:
+        nst *= d
+    o1 = (nseg + 3) // 4 * 4
+    o2 = o1 + nst * 4
+    seg = buf[:, :nseg].contiguous().reshape((n,) + tuple(seg_shape))
+    stats = buf[:, o1:o2].contiguous().view(torch.int32).reshape((n,) + tuple(stats_shape))
+    emb = buf[:, o2:].contiguous().view(torch.float32).reshape((n,) + tuple(emb_shape))
+    return seg, stats, emb
+
+
+def gather_records(seg: torch.Tensor, stats: torch.Tensor, emb: torch.Tensor, num_windows: int, world: int):
+    """The single data-path collective of the window-sharded mode: every rank contributes its packed per-window records
+    (binarised segmentations, frame counters, embeddings); -> the three tensors for all `num_windows` windows."""
+    buf = gather_windows(pack_records(seg, stats, emb), num_windows, world)
+    return unpack_records(buf, seg.shape[1:], stats.shape[1:], emb.shape[1:])

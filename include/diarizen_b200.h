@@ -192,6 +192,16 @@ int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream);
 /* scipy linkage(method="centroid") from the distance matrix (destroyed); Z [N-1][4] float64 */
 int64_t dz_linkage_workspace_bytes(int N);
 int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream);
+/* Flat clusters from the dendrogram of dz_linkage_centroid, selected as AgglomerativeClustering.cluster selects them
+ * (pyannote-audio/pyannote/audio/pipelines/clustering.py:418-492): cut at `threshold` (scipy fcluster, criterion "distance");
+ * when the number of clusters with >= min_cluster_size members falls outside [min_clusters, max_clusters] (or differs from
+ * num_clusters > 0) the cut moves to the merge iteration the reference's search stops at.  labels [N] int32 are
+ * scipy's fcluster numbers - 1 (before the small-cluster re-assignment); info [8] int32 = {large clusters, selected
+ * iteration or -1, "found only" flag, flat clusters, large clusters at the threshold, target, 0, 0}.
+ * force_iteration >= 0 cuts after that merge unconditionally (test hook), -1 otherwise. */
+int64_t dz_dendrogram_cut_workspace_bytes(int N);
+int dz_dendrogram_cut(const double* z_dev, int N, double threshold, int min_cluster_size, int min_clusters, int max_clusters,
+                      int num_clusters, int force_iteration, int32_t* labels_dev, int32_t* info_dev, void* workspace_dev, void* stream);
 /* per-chunk constrained assignment maximising the summed soft score (clustering.py:159-173); hard [C][S] int8, -2 = none */
 int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream);
 

@@ -1,0 +1,142 @@
+"""The CUDA path against golden vectors produced by the REFERENCE'S OWN glue code (scripts/make_glue_golden.py runs the
+unmodified pyannote-audio / diarizen files behind third-party stubs, oracle/ref_glue.py):
+  * full pipeline (both networks on the GPU) on the e2e goldens: identical segmentations, count, clusters, RTTM text;
+  * stage 2 (median, counting, clustering incl. the re-cut branches and VBx, reconstruction, RTTM) on the scripted goldens;
+  * the clustering classes on the reference classes' direct outputs (incl. > 32 clusters);
+  * dz_dendrogram_cut against scipy.fcluster at recording scale (shared-memory and global-memory variants)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _params(z, key):
+    return eval(str(z[key]), {"__builtins__": {}}, {"dict": dict})
+
+
+@pytest.mark.parametrize("arch", ["tiny_base", "tiny_large"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16"])
+def test_e2e_identical_rttm(arch, precision):
+    """waveform -> RTTM on the GPU == the reference's DiariZenPipeline.__call__ around the pinned network oracles."""
+    from diarizen_b200.pipeline import DiariZenPipeline
+    z = np.load(os.path.join(G, f"glue_e2e_{arch}.npz"))
+    pipe = DiariZenPipeline.from_random_init(arch, seed=int(z["weights_seed"]), seg_duration=float(z["seg_duration"]), batch_size=16,
+                                             min_cluster_size=int(z["min_cluster_size"]), classifier_gain=float(z["classifier_gain"]),
+                                             precision=precision)
+    wav = torch.from_numpy(z["wav_i16"].astype(np.float32) / 32768.0)
+    ann = pipe(dict(waveform=wav[None], sample_rate=16000), sess_name="sess")
+    res = pipe.last
+    seg = res["segmentations"].cpu().numpy()
+    flips = np.argwhere(seg != z["segmentations"])
+    assert flips.size == 0, f"{precision}: {len(flips)} frame decisions differ, first at (chunk, frame, speaker) = {flips[:5].tolist()}"
+    assert np.array_equal(res["count"].cpu().numpy(), z["count"])
+    assert np.array_equal(res["hard_clusters"], z["hard_clusters"])
+    assert np.array_equal(res["discrete"], z["discrete"])
+    assert ann.to_rttm() == str(z["rttm"])
+
+
+def _synth_cases():
+    out = []
+    for name in ("5s", "16s"):
+        z = np.load(os.path.join(G, f"glue_synth_{name}.npz"))
+        out += [(name, str(v)) for v in z["variants"]]
+    return out
+
+
+@pytest.mark.parametrize("name,variant", _synth_cases())
+def test_stage2_on_reference_goldens(name, variant, tmp_path):
+    from diarizen_b200.pipeline import DiariZenPipeline
+    z = np.load(os.path.join(G, f"glue_synth_{name}.npz"))
+    kw = _params(z, f"{variant}__params")
+    vbx = None
+    if "vbx" in kw:
+        from vbx_util import write_plda
+        write_plda(str(tmp_path), seed=int(z["plda_seed"]))
+        vbx = dict(kw["vbx"], plda_dir=str(tmp_path))
+    pipe = DiariZenPipeline.from_random_init("tiny_base", seed=0, seg_duration=float(z["seg_duration"]), batch_size=8,
+                                             min_cluster_size=kw.get("min_cluster_size", 30), ahc_threshold=kw["ahc_threshold"],
+                                             min_speakers=kw["min_speakers"], max_speakers=kw["max_speakers"],
+                                             apply_median_filtering=kw.get("apply_median_filtering", True), vbx=vbx)
+    emb = z[f"{variant}__embeddings"] if f"{variant}__embeddings" in z.files else z["embeddings"]
+    seg_exp = z[f"{variant}__segmentations"] if f"{variant}__segmentations" in z.files else z["segmentations"]
+    res = pipe.diarize_segmentations(z["raw_segmentations"], emb)
+    assert np.array_equal(res["segmentations"].cpu().numpy(), seg_exp)
+    assert np.array_equal(res["count"].cpu().numpy(), np.minimum(z[f"{variant}__count"], kw["max_speakers"]))
+    assert np.array_equal(res["hard_clusters"], z[f"{variant}__hard_clusters"])
+    assert np.array_equal(res["discrete"], z[f"{variant}__discrete"])
+    assert pipe.to_annotation(res["discrete"], "sess").to_rttm() == str(z[f"{variant}__rttm"])
+
+
+def _clu_names():
+    return [str(n) for n in np.load(os.path.join(G, "glue_clustering.npz"))["names"]]
+
+
+@pytest.mark.parametrize("name", _clu_names())
+def test_clustering_classes_on_reference_goldens(name, tmp_path):
+    from diarizen_b200 import clustering as cl
+    z = np.load(os.path.join(G, "glue_clustering.npz"))
+    prm = _params(z, f"{name}__params")
+    emb, seg = z[f"{name}__embeddings"], z[f"{name}__segmentations"].astype(np.float32)
+    if "vbx" in prm:
+        from vbx_util import write_plda
+        write_plda(str(tmp_path), seed=int(z["plda_seed"]))
+        v = prm["vbx"]
+        a = cl.VBxClustering(plda_dir=str(tmp_path), lda_dim=v["lda_dim"], maxIters=v["maxIters"])
+        a.ahc_criterion, a.ahc_threshold, a.Fa, a.Fb = v["ahc_criterion"], v["ahc_threshold"], v["Fa"], v["Fb"]
+        hard, soft, cent = a(emb, seg, min_clusters=1, max_clusters=20)
+    else:
+        a = cl.AgglomerativeClustering()
+        a.threshold, a.min_cluster_size = prm["threshold"], prm["mcs"]
+        hard, soft, cent = a(emb, seg, num_clusters=prm.get("num"), min_clusters=prm["min"], max_clusters=prm["max"])
+    assert np.array_equal(np.asarray(hard).astype(np.int16), z[f"{name}__hard"])
+    assert np.allclose(soft, z[f"{name}__soft"], atol=1e-8, equal_nan=True)
+    assert np.allclose(cent, z[f"{name}__centroids"], atol=1e-8)
+
+
+@pytest.mark.parametrize("n,method", [(8964, "centroid"), (15000, "single"), (2, "centroid"), (37, "centroid")])
+def test_dendrogram_cut_matches_scipy(n, method):
+    """labels == scipy.fcluster - 1 for threshold cuts and for iteration cuts; n = 15000 takes the global-memory variant."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from diarizen_b200 import _lib
+    r = np.random.default_rng(n)
+    x = (r.standard_normal((7, 32))[r.integers(0, 7, n)] + 0.6 * r.standard_normal((n, 32))).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    Z = linkage(x, method=method, metric="euclidean")
+    L = _lib.lib()
+    vp = C.c_void_p
+    dZ = torch.as_tensor(Z, device="cuda")
+    labels = torch.empty(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(8, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(L.dz_dendrogram_cut_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    _Z = Z.copy()
+    _Z[:, 2] = np.arange(n - 1)
+    hs = np.sort(Z[:, 2])
+    for t in [0.0, float(hs[len(hs) // 3]), float(hs[-max(1, min(6, n - 1))]), 10.0]:
+        _lib.check(L.dz_dendrogram_cut(vp(dZ.data_ptr()), n, t, 1, 1, n, 0, -1, vp(labels.data_ptr()), vp(info.data_ptr()), vp(ws.data_ptr()), None))
+        ref = fcluster(Z, t, criterion="distance") - 1
+        assert np.array_equal(labels.cpu().numpy(), ref), (n, t)
+        assert int(info[3]) == ref.max() + 1
+    for it in sorted({0, (n - 1) // 2, n - 2}):
+        _lib.check(L.dz_dendrogram_cut(vp(dZ.data_ptr()), n, 0.7, 1, 1, n, 0, it, vp(labels.data_ptr()), vp(info.data_ptr()), vp(ws.data_ptr()), None))
+        assert np.array_equal(labels.cpu().numpy(), fcluster(_Z, it, criterion="distance") - 1), (n, it)
+
+
+def test_dendrogram_cut_selection_matches_host_logic():
+    """min / max / num_clusters searches at recording scale: the device kernel (1024 threads, block reductions) picks the same
+    iteration and labels as the pinned glue oracle's loop over scipy.fcluster."""
+    from oracle import pipeline_oracle as po
+    from diarizen_b200.clustering import AgglomerativeClustering
+    r = np.random.default_rng(3)
+    n = 1500
+    x = (r.standard_normal((9, 256))[r.choice(9, n, p=[.3, .25, .2, .1, .05, .04, .03, .02, .01])] + 0.45 * r.standard_normal((n, 256))).astype(np.float32)
+    for mcs, lo, hi, num in [(30, 1, 20, None), (30, 1, 3, None), (30, 12, 20, None), (5, 1, 20, 4), (1, 1, 20, None), (30, 1, 1000, 7)]:
+        a = AgglomerativeClustering()
+        a.threshold, a.min_cluster_size = 0.7, mcs
+        got = a.cluster(x.copy(), lo, hi, num)
+        ref = po.ahc_cluster(x.copy(), 0.7, mcs, lo, hi, num)
+        assert np.array_equal(got, ref), (mcs, lo, hi, num, a.last_cut)

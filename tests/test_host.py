@@ -100,7 +100,36 @@ def _shard_worker(rank, world, port, q):
     for c in range(a, b):
         local[c - a] = c + 1
     full = gather_windows(local, Cn, world)
-    q.put((rank, full.numpy()))
+    # the packed per-window records of the sharded pipeline: one collective for segmentations + counters + embeddings
+    from diarizen_b200.sharding import gather_records
+    seg = torch.zeros((per, T, 4), dtype=torch.uint8)
+    stats = torch.zeros((per, 4, 2), dtype=torch.int32)
+    emb = torch.zeros((per, 4, 5), dtype=torch.float32)
+    for c in range(a, b):
+        seg[c - a] = c % 2
+        stats[c - a] = 1000 * c + torch.arange(8, dtype=torch.int32).view(4, 2)
+        emb[c - a] = c + 0.25
+    calls = []
+    orig = dist.all_gather_into_tensor
+    dist.all_gather_into_tensor = lambda *a_, **k_: (calls.append(1), orig(*a_, **k_))[1]
+    g = gather_records(seg, stats, emb, Cn, world)
+    dist.all_gather_into_tensor = orig
+    ok = (len(calls) == 1 and g[0].shape == (Cn, T, 4) and g[1].dtype == torch.int32 and g[2].dtype == torch.float32
+          and all(int(g[0][c].max()) == c % 2 and int(g[1][c, 3, 1]) == 1000 * c + 7 and float(g[2][c, 0, 0]) == c + 0.25 for c in range(Cn)))
+    # dispatch policy for several recordings (diarize_many): whole recordings round-robin, the remainder window-sharded with a rotating root
+    from diarizen_b200.pipeline import DiariZenPipeline
+    log = []
+
+    class Fake(DiariZenPipeline):
+        def __init__(self):
+            self.rttm_out_dir = None
+
+        def diarize_waveform(self, wav, shard=None, root=0):
+            log.append((int(wav[0]), shard, root))
+            return {"discrete": np.zeros((3, 1), dtype=np.uint8)} if (shard is False or rank == root) else {}
+
+    outs = Fake().diarize_many([torch.full((4,), float(i)) for i in range(5)], [f"r{i}" for i in range(5)])
+    q.put((rank, full.numpy(), ok, log, [o is not None for o in outs]))
     dist.destroy_process_group()
 
 
@@ -112,11 +141,16 @@ def test_window_sharding_gloo_world2():
     ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    outs = dict(q.get(timeout=120) for _ in range(2))
+    got = [q.get(timeout=120) for _ in range(2)]
     for p in ps:
         p.join(timeout=60)
+    outs = {g[0]: g for g in got}
     expect = np.repeat(np.arange(1, 12, dtype=np.uint8)[:, None], 7, axis=1)
-    assert np.array_equal(outs[0], expect) and np.array_equal(outs[1], expect)
+    assert np.array_equal(outs[0][1], expect) and np.array_equal(outs[1][1], expect)
+    assert outs[0][2] and outs[1][2], "packed record gather"
+    # 5 recordings on 2 ranks: 0..3 whole (rank = index mod 2, no collective), recording 4 sharded with root 4 % 2 = 0
+    assert outs[0][3] == [(0, False, 0), (2, False, 0), (4, True, 0)] and outs[1][3] == [(1, False, 0), (3, False, 0), (4, True, 0)]
+    assert outs[0][4] == [True, False, True, False, True] and outs[1][4] == [False, True, False, True, False]
 
 
 def test_load_waveform_resamples_other_rates(tmp_path):

@@ -101,7 +101,7 @@ def test_linkage_matches_scipy_bitwise(n, seed):
     assert np.array_equal(Z[:, 2], Zref[:, 2]), f"heights differ by {np.abs(Z[:, 2] - Zref[:, 2]).max():.3e}"
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 4, 7, 12])
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 7, 12, 31, 40, 127])
 def test_assign_matches_hungarian(K):
     from scipy.optimize import linear_sum_assignment
     from diarizen_b200.clustering import device_assign
@@ -113,6 +113,30 @@ def test_assign_matches_hungarian(K):
         r, k = linear_sum_assignment(soft[c], maximize=True)
         ref[r] = k
         assert np.array_equal(hard[c], ref), (c, hard[c], ref)
+
+
+def test_reconstruct_many_clusters():
+    """K > 32 clusters (int8 labels allow up to 127): the shared-memory variant of the reconstruction kernel."""
+    Cn, T, S, dur = 40, 249, 4, 5.0
+    step = 0.1 * dur
+    seg = _seg(Cn, T, S, 8)
+    segf = seg.astype(np.float32)
+    start = _starts(Cn, dur, step)
+    count_ref = po.speaker_count(segf, dur, step)
+    F = count_ref.shape[0]
+    rng = np.random.default_rng(9)
+    for K in (33, 60, 127):
+        hard = np.stack([rng.permutation(K)[:S] for _ in range(Cn)]).astype(np.int8)
+        hard[seg.sum(axis=1) == 0] = -2
+        hard[:, 0] = K - 1                                   # make sure the last cluster exists
+        cnt = np.minimum(count_ref, 3).astype(np.int8)
+        ref = po.reconstruct(segf, hard, cnt, dur, step)
+        dd = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib().dz_reconstruct(vp(torch.as_tensor(seg, device="cuda").data_ptr()), vp(torch.as_tensor(hard, device="cuda").data_ptr()),
+                                             vp(torch.as_tensor(start, device="cuda").data_ptr()),
+                                             vp(torch.as_tensor(cnt[:, 0].astype(np.uint8), device="cuda").data_ptr()), Cn, T, S, K, K, F,
+                                             vp(dd.data_ptr()), None, None))
+        assert np.array_equal(dd.cpu().numpy().astype(np.float64), ref), K
 
 
 def test_clustering_call_matches_oracle():

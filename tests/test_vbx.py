@@ -67,8 +67,9 @@ def test_fcluster_maxclust_equals_scipy(seed):
     n = int(r.integers(3, 120))
     x = r.standard_normal((n, 6)) + 3.0 * r.integers(0, 4, size=(n, 1))
     Z = linkage(x, method="centroid", metric="euclidean")
-    for t in [1, 2, 3, 5, 9, 30]:
-        np.testing.assert_array_equal(fcluster_maxclust(Z, t), fcluster(Z, t, criterion="maxclust"))
+    for t in [1, 2, 3, 5, 9, 30, n - 2, n - 1, n, n + 1, n + 2]:
+        if t >= 1:
+            np.testing.assert_array_equal(fcluster_maxclust(Z, t), fcluster(Z, t, criterion="maxclust"))
 
 
 def test_vbx_call_oracle_runs_and_separates():
