@@ -27,6 +27,33 @@ class Segment:
         return f"[{self.start:.3f} --> {self.end:.3f}]"
 
 
+@dataclass(frozen=True)
+class SlidingWindow:
+    """frame geometry (pyannote.core.SlidingWindow semantics): frame i covers [start + i * step, start + i * step + duration)"""
+    start: float
+    duration: float
+    step: float
+
+    def __getitem__(self, i: int) -> Segment:
+        return Segment(self.start + i * self.step, self.start + i * self.step + self.duration)
+
+    def closest_frame(self, t: float) -> int:
+        import numpy as np
+        return int(np.rint((t - self.start - 0.5 * self.duration) / self.step))
+
+
+@dataclass(frozen=True)
+class Specifications:
+    """the fields of the reference's task specifications that callers of the pipeline read
+    (pyannote-audio/pyannote/audio/core/task.py:79-136; diarizen/pipelines/inference.py:93)"""
+    duration: float
+    classes: tuple
+    powerset_max_classes: int
+    powerset: bool = True
+    permutation_invariant: bool = True
+    warm_up: tuple = (0.0, 0.0)
+
+
 class Annotation:
     def __init__(self, uri: Optional[str] = None):
         self.uri = uri

@@ -73,3 +73,39 @@ def select_checkpoints(val_metric_lst: List[Dict], val_metric: str = "Loss", val
     if len(sel) != avg_ckpt_num:
         raise AssertionError(f"selected {len(sel)} checkpoints, wanted {avg_ckpt_num}")
     return sel
+
+
+def write_hub_snapshot(root: Union[str, Path], arch, seg_state_dict: Dict[str, torch.Tensor], emb_state_dict: Dict[str, torch.Tensor],
+                       inference_args: Dict, clustering_args: Dict, plda: tuple = None) -> Path:
+    """Saves a model pair in the directory layout `DiariZenPipeline(diarizen_hub=...)` / `from_pretrained(<dir>)` read
+    (diarizen/pipelines/inference.py:34-50,95-119): `config.toml`, `pytorch_model.bin` (full segmentation state dict),
+    `<arch>.pt` = the WavLM `{config, state_dict}` checkpoint `model.args.wavlm_src` points at
+    (model_wavlm_conformer.py:209-221), `wespeaker/pytorch_model.bin` in the lightning `{"state_dict": ...}` wrapping
+    (core/model.py:460-473) and, when `plda = (xvec_transform dict, plda dict)` is given, `plda/*.npz` for VBx."""
+    import numpy as np
+    from .archs import to_reference_config
+    root = Path(root)
+    (root / "wespeaker").mkdir(parents=True, exist_ok=True)
+    torch.save(dict(seg_state_dict), root / "pytorch_model.bin")
+    src = root / f"{arch.name}.pt"
+    torch.save({"config": to_reference_config(arch),
+                "state_dict": {k[len("wavlm_model."):]: v for k, v in seg_state_dict.items() if k.startswith("wavlm_model.")}}, src)
+    torch.save({"state_dict": dict(emb_state_dict)}, root / "wespeaker" / "pytorch_model.bin")
+    if plda is not None:
+        (root / "plda").mkdir(exist_ok=True)
+        np.savez(root / "plda" / "xvec_transform.npz", **plda[0])
+        np.savez(root / "plda" / "plda.npz", **plda[1])
+
+    def table(d):
+        def val(v):
+            if isinstance(v, bool):
+                return "true" if v else "false"
+            if isinstance(v, str):
+                return '"' + v.replace("\\", "\\\\").replace('"', '\\"') + '"'
+            return repr(v)
+        return "".join(f"{k} = {val(v)}\n" for k, v in d.items())
+    head = {"attention_in": arch.head_dim_model, "ffn_hidden": arch.head_ffn, "num_head": arch.head_heads, "num_layer": arch.head_layers,
+            "kernel_size": arch.head_kernel, "wavlm_layer_num": arch.num_layers + 1, "wavlm_feat_dim": arch.embed_dim}
+    with open(root / "config.toml", "w") as f:
+        f.write(f"[model.args]\nwavlm_src = \"{src}\"\n{table(head)}\n[inference.args]\n{table(inference_args)}\n[clustering.args]\n{table(clustering_args)}")
+    return root

@@ -32,6 +32,7 @@ class EmbeddingModel:
             raise RuntimeError("diarizen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
         self._L = _lib.lib()
+        self._ctor = (state_dict, precision, gemm_impl, prefix)
         prec = {"bf16": 1, "fp16": 2, "bf16x3": 3}[precision]
         with torch.cuda.device(self.device):
             self._h = self._L.dz_emb_create(prec, {"tc": 0, "simt": 1}[gemm_impl])
@@ -49,6 +50,15 @@ class EmbeddingModel:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._L.dz_emb_destroy(h)
+
+    def to(self, device) -> "EmbeddingModel":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("diarizen_b200 runs on CUDA devices only (no CPU fallback)")
+        if device == self.device or (device.index is None and self.device.type == "cuda"):
+            return self
+        sd, precision, gi, prefix = self._ctor
+        return EmbeddingModel(sd, precision=precision, gemm_impl=gi, device=device, prefix=prefix)
 
     def embed_windows(self, waveforms: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         """waveforms (B, N) fp32, masks (B, S, T) -> (B, S, 256) fp32 on the device."""

@@ -149,13 +149,21 @@ class DiariZenPipeline:
                 arch = arch_from_reference_config(ck["config"], name=Path(src).stem)
             else:
                 arch = get_arch(src)
+            # conformer head hyper-parameters of Model.__init__ (model_wavlm_conformer.py:26-48), when the config names them
+            import dataclasses
+            head = {ours: int(margs[theirs]) for theirs, ours in (("attention_in", "head_dim_model"), ("ffn_hidden", "head_ffn"), ("num_head", "head_heads"),
+                                                                    ("num_layer", "head_layers"), ("kernel_size", "head_kernel")) if theirs in margs}
+            if head:
+                arch = dataclasses.replace(arch, **head)
             _seg = SegmentationModel(arch, sd, precision=precision, device=self.device)
         if _emb is None:
             esd = torch.load(str(embedding_model), map_location="cpu")
             esd = esd.get("state_dict", esd)
             _emb = EmbeddingModel(esd, precision=precision, device=self.device)
+        _seg.duration = self.seg_duration
         self._segmentation = _seg
         self._embedding = _emb
+        assert self._segmentation.model.specifications.powerset is True   # inference.py:93
         if rttm_out_dir is not None:
             os.makedirs(rttm_out_dir, exist_ok=True)
         self.rttm_out_dir = rttm_out_dir
@@ -165,6 +173,21 @@ class DiariZenPipeline:
         self._timing, self._t_last = {}, None
 
     # ------------------------------------------------------------------------------------------------
+    def to(self, device) -> "DiariZenPipeline":
+        """pyannote `Pipeline.to(device)` (pyannote-audio/pyannote/audio/core/pipeline.py:328-348): moves both models."""
+        if not isinstance(device, torch.device):
+            raise TypeError(f"`device` must be an instance of `torch.device`, got `{type(device).__name__}`")
+        self._segmentation = self._segmentation.to(device)
+        self._embedding = self._embedding.to(device)
+        self.device = self._segmentation.device
+        self.clustering.device = self.device
+        return self
+
+    @property
+    def model(self):
+        """the segmentation model, as `SpeakerDiarization.model` (speaker_diarization.py:136)"""
+        return self._segmentation
+
     @classmethod
     def from_pretrained(cls, repo_id: str, cache_dir: str = None, rttm_out_dir: str = None, **kw) -> "DiariZenPipeline":
         """`repo_id` may be a local directory laid out like the hub snapshot (config.toml, pytorch_model.bin and
@@ -220,30 +243,29 @@ class DiariZenPipeline:
     # ------------------------------------------------------------------------------------------------
     # stage 1 - every rank, on its own window range: the two networks and the per-window kernels between them
     # ------------------------------------------------------------------------------------------------
-    def _front(self, wdev: torch.Tensor, Cn: int, window: int, step: int, T: int, c0: int, c1: int, per: int):
-        """-> (seg (per,T,S) uint8 median-filtered, stats (per,S,2) int32, emb (per,S,256) fp32); rows >= c1-c0 are padding."""
+    def _front(self, wloc: torch.Tensor, n_loc: int, window: int, step: int, T: int, c0: int, c1: int, per: int):
+        """wloc: the samples of windows c0..c1-1.  -> (raw, seg (per,T,S) uint8 median-filtered, stats (per,S,2) int32,
+        emb (per,S,256) fp32); rows >= c1-c0 are padding."""
         dev, L, S = self.device, self._L, 4
-        st = vp(torch.cuda.current_stream(dev).cuda_stream)
-        chunks = wdev.as_strided((Cn, window), (step, 1))
-        n_loc = c1 - c0
+        chunks = wloc.as_strided((max(n_loc, 0), window), (step, 1))
         raw = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
         bs = self.engine_windows
         # The engines plan (workspace + tensor maps) per batch shape: the ragged last batch is padded to the full batch
         # size instead of triggering a re-plan (two multi-GB reallocations per recording otherwise).
-        for a in range(c0, c1, bs):
-            b = min(a + bs, c1)
+        for a in range(0, n_loc, bs):
+            b = min(a + bs, n_loc)
             if b - a == bs or n_loc < bs:
-                self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=raw[a - c0:b - c0])
+                self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=raw[a:b])
             else:
                 wpad = torch.zeros((bs, window), device=dev, dtype=torch.float32)
                 wpad[:b - a] = chunks[a:b]
                 tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
                 self._segmentation.hard(wpad, want_logp=False, ml_out=tail)
-                raw[a - c0:b - c0] = tail[:b - a]
+                raw[a:b] = tail[:b - a]
         self._mark("segmentation")
-        return (raw,) + self._masks_and_embeddings(raw, wdev, chunks, window, step, T, c0, c1, per)
+        return (raw,) + self._masks_and_embeddings(raw, wloc, chunks, window, step, T, c0, c1, per)
 
-    def _masks_and_embeddings(self, raw, wdev, chunks, window, step, T, c0, c1, per):
+    def _masks_and_embeddings(self, raw, wloc, chunks, window, step, T, c0, c1, per):
         dev, L, S = self.device, self._L, 4
         st = vp(torch.cuda.current_stream(dev).cuda_stream)
         if self.apply_median_filtering:
@@ -257,23 +279,24 @@ class DiariZenPipeline:
         _lib.check(L.dz_embedding_masks(vp(seg.data_ptr()), per, T, S, min_num_frames, vp(masks.data_ptr()), vp(stats.data_ptr()), st))
         # chunk crops as the reference computes them (io.py:359-364): start = floor(c * step_s * sr) in float64
         chunk_step_s = self.segmentation_step * self.seg_duration
-        e_starts = [int(math.floor((c * chunk_step_s) * SR)) for c in range(c0, c1)]
-        same = all(e == c * step for e, c in zip(e_starts, range(c0, c1)))
+        e_starts = [int(math.floor((c * chunk_step_s) * SR)) - c0 * step for c in range(c0, c1)]   # relative to wloc
+        same = all(e == i * step for i, e in enumerate(e_starts))
         self._mark("count_masks")
         emb = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
         ebs = self.engine_emb_windows
         n_loc = c1 - c0
-        for a in range(c0, c1, ebs):
-            b = min(a + ebs, c1)
+        for a in range(0, n_loc, ebs):
+            b = min(a + ebs, n_loc)
             if same:
                 wv = chunks[a:b].contiguous()
             else:
-                wv = torch.stack([wdev[e_starts[c - c0]:e_starts[c - c0] + window] for c in range(a, b)])
-            mk = masks[a - c0:b - c0]
+                wv = torch.stack([torch.nn.functional.pad(wloc[max(e_starts[i], 0):e_starts[i] + window], (0, max(0, e_starts[i] + window - wloc.shape[0])))[:window]
+                                  for i in range(a, b)])
+            mk = masks[a:b]
             if b - a < ebs and n_loc >= ebs:   # pad the ragged last batch (see above)
                 wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
                 mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
-            emb[a - c0:b - c0] = self._embedding.embed_windows(wv, mk)[:b - a]
+            emb[a:b] = self._embedding.embed_windows(wv, mk)[:b - a]
         self._mark("embedding")
         return seg, stats, emb
 
@@ -345,14 +368,17 @@ class DiariZenPipeline:
             Nw = wav.shape[0]
             window, step, Cn = self._windows(Nw)
             T = self._segmentation.num_frames(window)
-            pad_to = (Cn - 1) * step + window
-            if wav.device == dev and wav.dtype == torch.float32 and Nw >= pad_to:
-                wdev = wav
-            else:
-                wdev = torch.zeros(max(pad_to, Nw), device=dev, dtype=torch.float32)
-                wdev[:Nw] = wav.to(dev, torch.float32, non_blocking=True)
             c0, c1, per = window_range(Cn, rank, world)
-            _, seg, stats, emb = self._front(wdev, Cn, window, step, T, c0, c1, per)
+            # this rank's span of the recording: windows c0..c1-1 (zero padded past the end for the orphan chunk)
+            s0, s1 = c0 * step, (max(c1, c0 + 1) - 1) * step + window
+            if wav.device == dev and wav.dtype == torch.float32 and Nw >= s1:
+                wloc = wav[s0:s1]
+            else:
+                wloc = torch.zeros(s1 - s0, device=dev, dtype=torch.float32)
+                if Nw > s0:
+                    wloc[:min(Nw, s1) - s0] = wav[s0:min(Nw, s1)].to(dev, torch.float32, non_blocking=True)
+            self.last_h2d_bytes = 0 if wav.device == dev else 4 * max(0, min(Nw, s1) - s0)
+            _, seg, stats, emb = self._front(wloc, c1 - c0, window, step, T, c0, c1, per)
             if world > 1:
                 seg, stats, emb = gather_records(seg, stats, emb, Cn, world)
                 self._mark("all_gather")

@@ -45,6 +45,7 @@ class SegmentationModel:
         self.arch = arch
         self.device = torch.device(device if device is not None else "cuda")
         self.precision = precision
+        self._ctor = (state_dict, gemm_impl, attn_impl)
         self._L = _lib.lib()
         prec = {"bf16": 1, "fp16": 2, "bf16x3": 3}[precision]
         with torch.cuda.device(self.device):
@@ -74,6 +75,39 @@ class SegmentationModel:
 
     def num_frames(self, num_samples: int) -> int:
         return self.arch.num_frames(num_samples)
+
+    # --- the attributes of the reference `Model` / `Inference` objects that pipeline callers read (inference.py:93,140) ---
+    @property
+    def model(self) -> "SegmentationModel":
+        """`pipeline._segmentation.model` in the reference is the nn.Module inside the Inference wrapper; here both are this object"""
+        return self
+
+    @property
+    def specifications(self):
+        from .annotation import Specifications
+        return Specifications(duration=getattr(self, "duration", 16.0), classes=tuple(f"speaker#{i + 1}" for i in range(NUM_SPEAKERS)),
+                              powerset_max_classes=2)
+
+    @property
+    def _receptive_field(self):
+        """SlidingWindow of the conv stack (core/model.py:180-195 evaluated with the reference's receptive_field.py helpers for
+        kernels [10,3,3,3,3,2,2] / strides [5,2,2,2,2,2,2]): 400-sample frames every 320 samples, the centre the helpers return
+        for frame 0 is sample 79 -> start = (79 - 199.5) / 16000 s"""
+        from .annotation import SlidingWindow
+        return SlidingWindow(start=(79 - (400 - 1) / 2) / 16000, duration=400 / 16000, step=320 / 16000)
+
+    def eval(self) -> "SegmentationModel":
+        return self
+
+    def to(self, device) -> "SegmentationModel":
+        """-> this model when it already lives on `device`, else a new engine built there from the same weights"""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("diarizen_b200 runs on CUDA devices only (no CPU fallback)")
+        if device == self.device or (device.index is None and self.device.type == "cuda"):
+            return self
+        sd, gi, ai = self._ctor
+        return SegmentationModel(self.arch, sd, precision=self.precision, gemm_impl=gi, attn_impl=ai, device=device)
 
     def _prep(self, waveforms: torch.Tensor) -> torch.Tensor:
         if waveforms.dim() == 3:
