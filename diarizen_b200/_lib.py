@@ -44,6 +44,7 @@ class GemmDesc(C.Structure):
         ("res16", C.c_void_p),
         ("res16_plane", C.c_int64), ("res16_bstride", C.c_int64),
         ("ldr16", C.c_int32), ("res16_row_off", C.c_int32),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("_pad3", C.c_int32),
     ]
 
     @classmethod

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
 }
 
 cudaError_t gemm_simt_launch(const GemmDesc& d, cudaStream_t st) {
+  if (d.ln_gamma != nullptr) return cudaErrorNotSupported;   // the fused row LayerNorm exists in the tcgen05 epilogue only
   dim3 grid((d.M + SM_ROWS - 1) / SM_ROWS, d.groups > 1 ? d.groups : (max(d.N, d.zero_pad_to) + SM_COLS - 1) / SM_COLS,
             d.batches);
   gemm_simt_kernel<<<grid, 256, 0, st>>>(d);

@@ -601,6 +601,35 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
       }
       mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
       tc_fence_after();
+      // Row LayerNorm fused into the epilogue (conv stack of the layer-norm extractor: components.py:119-122): the tile spans
+      // the whole output row (N <= BN) and a thread owns one accumulator row, so mean and variance are two thread-local
+      // sweeps over its TMEM lane; both warps of a lane quarter compute them (TMEM reads are cheap) and normalise their own spans.
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (d.ln_gamma != nullptr) {
+        const int ngrp = (d.N + 31) >> 5;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < ngrp; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + (uint32_t)(g * 32), r);
+          tmem_ld_wait();
+          const int nrem = d.N - g * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum += (j < nrem) ? __uint_as_float(r[j]) : 0.f;
+        }
+        ln_mean = sum / (float)d.N;
+        float ssq = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < ngrp; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + (uint32_t)(g * 32), r);
+          tmem_ld_wait();
+          const int nrem = d.N - g * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float c = __uint_as_float(r[j]) - ln_mean; ssq += (j < nrem) ? c * c : 0.f; }
+        }
+        ln_rstd = rsqrtf(ssq / (float)d.N + d.ln_eps);
+      }
 #pragma unroll 1
       for (int s = par; s < nspans; s += 2, ++sc) {
         const int buf = dbl ? (int)(sc & 1) : 0;
@@ -634,6 +663,14 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (d.ln_gamma != nullptr) {
+            const int nv = d.N - (col0 + g * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float ga = (j < nv) ? __ldg(d.ln_gamma + gcol + j) : 0.f, be = (j < nv) ? __ldg(d.ln_beta + gcol + j) : 0.f;
+              v[j] = (v[j] - ln_mean) * ln_rstd * ga + be;
+            }
+          }
           switch (pre_act) {
             case 1: epi_math32<1>(v, bp, d.alpha); break;
             case 2: epi_math32<2>(v, bp, d.alpha); break;
@@ -838,7 +875,7 @@ static cudaError_t launch_bn_tma(const GemmPlan* p, cudaStream_t st) {
 // the same kind as the output (or none).  Everything else takes the generic epilogue.
 static bool tma_epilogue_eligible(const GemmDesc& d) {
   static const bool off = (getenv("DZ_GEMM_LEGACY_EPILOGUE") != nullptr);
-  if (off) return false;
+  if (off && d.ln_gamma == nullptr) return false;
   if (d.groups != 1 || d.out_t != nullptr) return false;
   const bool f = d.out_f32 != nullptr, h = d.out_bf != nullptr;
   if (f == h) return false;
@@ -867,6 +904,13 @@ GemmPlan* gemm_plan_create(const GemmDesc& d, int force_bn) {
     if (force_bn == 0) p->bn = 128; else want_tma = false;
   }
   if (d.groups > 1 && d.N > p->bn) { g_err = "grouped GEMM needs N <= BN"; delete p; return nullptr; }
+  if (d.ln_gamma != nullptr) {
+    // the fused row LayerNorm needs the whole row in one accumulator tile and the register (TMA-store) epilogue
+    if (d.N > 128 && force_bn == 0) p->bn = 256;
+    if (d.N > p->bn || !want_tma || d.bias != nullptr || d.residual != nullptr || d.res16 != nullptr || d.ln_beta == nullptr || d.act_after_res) {
+      g_err = "fused LayerNorm epilogue needs N <= tile width, one plain output, no bias / residual"; delete p; return nullptr;
+    }
+  }
   if (d.npass != 1 && d.npass != 3) { g_err = "npass must be 1 or 3"; delete p; return nullptr; }
   p->rank5 = (d.conv_runs == 0 && d.a_kinner != d.K) ? 1 : 0;
   const long long rows_alloc = d.a_rows_alloc > 0 ? d.a_rows_alloc : d.M;

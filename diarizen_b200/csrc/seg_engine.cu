@@ -453,7 +453,15 @@ static int plan_impl(dz_seg* s, int B, int N) {
     d.a_bstride = (long long)Tl[l - 1] * Cp[l - 1]; d.a_rows_alloc = Tl[l];
     d.b = W.w.p; d.b_plane = W.plane; d.ldb = W.ldb; d.b_gstride = W.gstride;
     const bool last = (l == 6);
-    if (large) {
+    static const bool ln_unfused = [] { const char* e = getenv("DZ_CONV_LN_UNFUSED"); return e && e[0] == '1'; }();
+    if (large && !last && !ln_unfused && s->gemm_impl == 0 && W.N <= 256) {
+      // conv -> LayerNorm(channels) -> GELU in one launch: the accumulator tile holds whole rows (N <= 256), so the
+      // normalisation happens on the TMEM row before the 16-bit planes are stored (no fp32 round trip through HBM)
+      d.ln_gamma = s->conv_gamma[l].as<float>(); d.ln_beta = s->conv_beta[l].as<float>(); d.ln_eps = 1e-5f; d.act = 1;
+      d.out_bf = out.p; d.ob_plane = out.plane; d.ldob = Cp[l]; d.ob_bstride = (long long)Tl[l] * Cp[l]; d.zero_pad_to = Cp[l];
+      d.out_planes = P;
+      p.gemm("conv" + std::to_string(l), d);
+    } else if (large) {
       d.out_f32 = convf; d.ldo = Cp[l]; d.of_bstride = (long long)Tl[l] * Cp[l];
       p.gemm("conv" + std::to_string(l), d);
       LnArgs ln{};

@@ -70,6 +70,12 @@ typedef struct dz_gemm_desc {
   const void* res16;
   int64_t res16_plane, res16_bstride;
   int32_t ldr16, res16_row_off;
+  /* optional row LayerNorm of the accumulator row (over the N valid columns, biased variance) applied before the activation:
+   * v = (acc - mean) * rstd * ln_gamma[col] + ln_beta[col].  tcgen05 path only, N <= tile width (256), no bias / residual. */
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  int32_t _pad3;
 } dz_gemm_desc;
 
 /* impl: 0 = tcgen05 tensor-core kernel, 1 = CUDA-core checker kernel.  force_bn: 0 auto, or 64/128/256. */

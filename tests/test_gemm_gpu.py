@@ -193,3 +193,39 @@ def test_conv2d_as_gemm(impl, npass, B, H, W, Cin, Cout, ks, stride, res):
     got = (out[0].double() + out[1].double()).view(B, Ho, Wop, Cout)
     _check("conv2d", got[:, :, 1:Wo + 1], ref, npass if npass == 1 else 3)
     assert (got[:, :, 0] == 0).all() and (got[:, :, -1] == 0).all(), "zero border must stay untouched"
+
+
+@pytest.mark.parametrize("npass", [1, 3])
+@pytest.mark.parametrize("B,Tin,Cin,Cout", [(2, 1000, 153, 224), (2, 777, 512, 153), (3, 401, 24, 40), (1, 300, 224, 255)])
+def test_conv1d_with_fused_layernorm_gelu(npass, B, Tin, Cin, Cout):
+    """conv1d -> LayerNorm(channels) -> GELU in ONE launch (row LayerNorm on the accumulator row in TMEM): the conv stack of
+    the layer-norm feature extractor (components.py:119-122)."""
+    torch.manual_seed(Tin + Cout)
+    dev, k = "cuda", 3
+    x = torch.randn(B, Tin, Cin, device=dev)
+    w = torch.randn(Cout, Cin, k, device=dev) / (Cin * k) ** 0.5
+    gamma = 1.0 + 0.2 * torch.randn(Cout, device=dev)
+    beta = 0.3 * torch.randn(Cout, device=dev)
+    Cp = rup(Cin, 8)
+    xp = to_planes(x, Cp)
+    wr = torch.zeros(Cout, k, Cp, device=dev)
+    wr[:, :, :Cin] = w.permute(0, 2, 1)
+    wp = to_planes(wr.reshape(Cout, k * Cp))
+    Tout = (Tin - k) // 2 + 1
+    ldo = rup(Cout, 8)
+    out_b = torch.full((2, B, Tout, ldo), 7.0, device=dev, dtype=torch.bfloat16)
+    d = _lib.GemmDesc.default()
+    d.M, d.N, d.K, d.npass, d.batches = Tout, Cout, k * Cp, npass, B
+    d.a, d.a_plane, d.a_rstride, d.a_kinner, d.a_bstride, d.a_rows_alloc = ptr(xp).value, xp[0].numel(), 2 * Cp, k * Cp, Tin * Cp, Tout
+    d.b, d.b_plane, d.ldb, d.b_gstride = ptr(wp).value, wp[0].numel(), wp.shape[-1], wp[0].numel()
+    d.act = 1
+    d.ln_gamma, d.ln_beta, d.ln_eps = ptr(gamma).value, ptr(beta).value, 1e-5
+    d.out_bf, d.ob_plane, d.ldob, d.ob_bstride, d.out_planes, d.zero_pad_to = ptr(out_b).value, out_b[0].numel(), ldo, Tout * ldo, 2, ldo
+    run_gemm(d, 0)
+    xv = planes_value(xp, npass)[..., :Cin].permute(0, 2, 1)
+    wv = planes_value(wp, npass).reshape(Cout, k, Cp)[:, :, :Cin].permute(0, 2, 1)
+    y = torch.nn.functional.conv1d(xv, wv, stride=2).permute(0, 2, 1)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(y, (Cout,), gamma.double(), beta.double(), 1e-5))
+    got = out_b[0].double() + out_b[1].double()
+    _check("ln+gelu planes", got[..., :Cout], ref, 3 if npass == 3 else 1)
+    assert (out_b[..., Cout:ldo] == 0).all(), "pad columns must be zeroed"
