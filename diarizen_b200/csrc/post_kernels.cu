@@ -396,6 +396,29 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel_v2(double* __res
     if (tid == 0) { size[x] = 0; size[y] = nx + ny; cid[y] = N + step; nn[y] = ybest.i; nnd[y] = ybest.v; }
     __syncthreads();
     const int ntodo = s_ntodo;
+    if (ntodo <= 12) {
+      // few rows to rescan (the common case): the WHOLE block scans each of them - one batch of loads in flight per thread
+      // instead of ~N/128 dependent L2 round trips of a single warp; same candidates, same (distance, index) order
+      for (int q = 0; q < ntodo; ++q) {
+        const int i = todo[q];
+        const double* row = Dm + (long long)i * N;
+        ArgMin b2{INFINITY, 0x7fffffff};
+        for (int j0 = tid; j0 < N; j0 += 8 * nt) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int j = j0 + u * nt; v[u] = (j < N) ? row[j] : INFINITY; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nt;
+            if (j < N && j != i && size[j] > 0) b2 = amin(b2, ArgMin{v[u], j});
+          }
+        }
+        b2 = block_argmin(b2, sc);
+        if (tid == 0) { nn[i] = b2.i; nnd[i] = b2.v; }
+      }
+      __syncthreads();
+      continue;
+    }
     for (int q = tid >> 5; q < ntodo; q += nt >> 5) {
       const int i = todo[q];
       ArgMin b2{INFINITY, 0x7fffffff};

@@ -18,7 +18,6 @@ import ctypes as C
 import io
 import math
 import os
-import wave
 from pathlib import Path
 from typing import Any, Dict, Optional, Union
 
@@ -56,6 +55,48 @@ def _to_16k(w: torch.Tensor, sr: int) -> torch.Tensor:
     return AF.resample(w[None], sr, SR)[0].contiguous()
 
 
+def _read_wav(src):
+    """RIFF/WAVE decode on the host (stands in for torchaudio.load, which needs a codec backend that is not in this image):
+    PCM 8 / 16 / 24 / 32 bit, IEEE float 32 / 64, plain and WAVE_FORMAT_EXTENSIBLE headers.  -> ((frames, channels) float32 in
+    [-1, 1], sample rate).  Compressed formats (flac, mp3, ...) are not decoded here: pass {"waveform", "sample_rate"}."""
+    import struct
+    raw = src.getvalue() if isinstance(src, io.BytesIO) else open(os.fspath(src), "rb").read()
+    if len(raw) < 12 or raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE file (compressed audio must be decoded by the caller and passed as {'waveform', 'sample_rate'})")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(raw):
+        cid, size = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        body = raw[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = body
+        elif cid == b"data":
+            data = body
+            break
+        pos += 8 + size + (size & 1)
+    if fmt is None or data is None:
+        raise ValueError("WAVE file without fmt / data chunk")
+    tag, nch, sr, _, align, bits = struct.unpack("<HHIIHH", fmt[:16])
+    if tag == 0xFFFE and len(fmt) >= 26:          # WAVE_FORMAT_EXTENSIBLE: the real tag is the first word of the sub-format GUID
+        tag = struct.unpack("<H", fmt[24:26])[0]
+    width = bits // 8
+    n = len(data) // (width * nch) * nch
+    if tag == 1 and width == 2:
+        x = np.frombuffer(data, dtype="<i2", count=n).astype(np.float32) / 32768.0
+    elif tag == 1 and width == 4:
+        x = np.frombuffer(data, dtype="<i4", count=n).astype(np.float32) / 2147483648.0
+    elif tag == 1 and width == 3:
+        b3 = np.frombuffer(data, dtype=np.uint8, count=3 * n).reshape(-1, 3).astype(np.int32)
+        v = b3[:, 0] | (b3[:, 1] << 8) | (b3[:, 2] << 16)
+        x = (v - ((v & 0x800000) << 1)).astype(np.float32) / 8388608.0
+    elif tag == 1 and width == 1:
+        x = (np.frombuffer(data, dtype=np.uint8, count=n).astype(np.float32) - 128.0) / 128.0
+    elif tag == 3 and width in (4, 8):
+        x = np.frombuffer(data, dtype="<f4" if width == 4 else "<f8", count=n).astype(np.float32)
+    else:
+        raise ValueError(f"unsupported WAVE encoding (format tag {tag}, {bits} bits)")
+    return x.reshape(-1, nch), sr
+
+
 def load_waveform(in_wav) -> torch.Tensor:
     """-> mono (N,) float32 in [-1, 1], 16 kHz.  Stands in for `torchaudio.load(in_wav)[0][0]` (inference.py:127-128)."""
     if isinstance(in_wav, dict):
@@ -66,18 +107,8 @@ def load_waveform(in_wav) -> torch.Tensor:
         w = w[0] if w.dim() == 2 else w
         return _to_16k(w, int(in_wav.get("sample_rate", SR)))
     if isinstance(in_wav, (str, os.PathLike, io.BytesIO)):
-        with wave.open(in_wav if isinstance(in_wav, io.BytesIO) else str(in_wav), "rb") as f:
-            sr, nch, sw, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
-            raw = f.readframes(n)
-        if sw == 2:
-            x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-        elif sw == 4:
-            x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-        elif sw == 1:
-            x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
-        else:
-            raise ValueError(f"unsupported sample width {sw}")
-        return _to_16k(torch.from_numpy(x.reshape(-1, nch)[:, 0].copy()), sr)   # force channel 0 (inference.py:128)
+        x, sr = _read_wav(in_wav)
+        return _to_16k(torch.from_numpy(x[:, 0].copy()), sr)   # force channel 0 (inference.py:128)
     raise TypeError(f"input must be either a str, BytesIO or a ProtocolFile; there was {type(in_wav)}")
 
 

@@ -177,3 +177,29 @@ def test_load_waveform_resamples_other_rates(tmp_path):
     assert int(spec.argmax()) == 440
     w2 = load_waveform({"waveform": torch.from_numpy(x)[None], "sample_rate": sr})
     assert w2.shape == (16000,)
+
+
+def test_wav_decoder_formats(tmp_path):
+    """24-bit PCM, 32-bit float and WAVE_FORMAT_EXTENSIBLE headers (what torchaudio.load accepts and the stdlib `wave` does not)."""
+    import io
+    import struct
+    from diarizen_b200.pipeline import load_waveform
+    sr, n = 16000, 800
+    x = (0.5 * np.sin(2 * np.pi * 300 * np.arange(n) / sr)).astype(np.float32)
+
+    def riff(fmt, data):
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" + b"data" + struct.pack("<I", len(data)) + data
+        return io.BytesIO(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+    i24 = np.round(x * 8388607).astype(np.int32)
+    d24 = b"".join(struct.pack("<i", int(v))[:3] for v in i24)
+    w = load_waveform(riff(struct.pack("<HHIIHH", 1, 1, sr, sr * 3, 3, 24), d24))
+    assert w.shape == (n,) and torch.allclose(w, torch.from_numpy(i24.astype(np.float32) / 8388608.0))
+    w = load_waveform(riff(struct.pack("<HHIIHH", 3, 1, sr, sr * 4, 4, 32), x.astype("<f4").tobytes()))
+    assert torch.equal(w, torch.from_numpy(x))
+    ext = struct.pack("<HHIIHH", 0xFFFE, 2, sr, sr * 4, 4, 16) + struct.pack("<HHI", 22, 16, 3) + struct.pack("<H", 1) + b"\x00" * 14
+    st = np.stack([np.round(x * 32767), np.zeros(n)], axis=1).astype("<i2")
+    w = load_waveform(riff(ext, st.tobytes()))
+    assert w.shape == (n,) and torch.allclose(w, torch.from_numpy(st[:, 0].astype(np.float32) / 32768.0))
+    with pytest.raises(ValueError):
+        load_waveform(io.BytesIO(b"fLaC" + b"\x00" * 40))
