@@ -55,9 +55,24 @@ class Specifications:
 
 
 class Annotation:
+    """Speaker turns.  Tracks added one by one (`ann[segment, track] = label`) and tracks handed over as arrays
+    (`Annotation.from_arrays`, what the pipeline does: a recording can hold 10^5 turns) live side by side; Segment objects
+    for the array part are only made when somebody iterates."""
+
     def __init__(self, uri: Optional[str] = None):
         self.uri = uri
         self._tracks: List[Tuple[Segment, int, object]] = []   # (segment, track, label) in insertion order
+        self._arr = None                                         # (starts, ends, tracks) float64 / float64 / int64 arrays
+
+    @classmethod
+    def from_arrays(cls, starts, ends, tracks, uri: Optional[str] = None) -> "Annotation":
+        """turns [starts[i], ends[i]) of integer track / label tracks[i]; empty ones (end - start <= 1e-6) are dropped"""
+        import numpy as np
+        ann = cls(uri)
+        starts, ends, tracks = np.asarray(starts, dtype=np.float64), np.asarray(ends, dtype=np.float64), np.asarray(tracks, dtype=np.int64)
+        keep = (ends - starts) > 1e-6
+        ann._arr = (starts[keep], ends[keep], tracks[keep])
+        return ann
 
     def __setitem__(self, key, label):
         segment, track = key
@@ -66,14 +81,21 @@ class Annotation:
         self._tracks.append((segment, track, label))
 
     def __len__(self) -> int:
-        return len(self._tracks)
+        return len(self._tracks) + (len(self._arr[0]) if self._arr is not None else 0)
+
+    def _all(self) -> List[Tuple[Segment, int, object]]:
+        out = list(self._tracks)
+        if self._arr is not None:
+            s, e, t = self._arr
+            out += [(Segment(float(a), float(b)), int(k), int(k)) for a, b, k in zip(s.tolist(), e.tolist(), t.tolist())]
+        return out
 
     def labels(self) -> list:
-        return sorted({l for _, _, l in self._tracks})
+        return sorted({l for _, _, l in self._all()}, key=str)
 
     def itertracks(self, yield_label: bool = False) -> Iterator:
         # segments in (start, end) order; tracks sharing a segment in the order of their names
-        for seg, trk, lab in sorted(self._tracks, key=lambda x: (x[0].start, x[0].end, str(x[1]), str(x[2]))):
+        for seg, trk, lab in sorted(self._all(), key=lambda x: (x[0].start, x[0].end, str(x[1]), str(x[2]))):
             yield (seg, trk, lab) if yield_label else (seg, trk)
 
     def to_rttm(self) -> str:

@@ -409,7 +409,8 @@ class DiariZenPipeline:
                 if Nw > s0:
                     wloc[:min(Nw, s1) - s0] = wav[s0:min(Nw, s1)].to(dev, torch.float32, non_blocking=True)
             self.last_h2d_bytes = 0 if wav.device == dev else 4 * max(0, min(Nw, s1) - s0)
-            _, seg, stats, emb = self._front(wloc, c1 - c0, window, step, T, c0, c1, per)
+            raw, seg, stats, emb = self._front(wloc, c1 - c0, window, step, T, c0, c1, per)
+            self.last_raw = raw[:c1 - c0]      # this rank's window decisions before the median filter (parity tests)
             if world > 1:
                 seg, stats, emb = gather_records(seg, stats, emb, Cn, world)
                 self._mark("all_gather")
@@ -477,27 +478,19 @@ class DiariZenPipeline:
         """Binarize(onset=0.5, offset=0.5) on a {0,1} matrix (pyannote-audio/pyannote/audio/utils/signal.py:254-317):
         a region starts at the middle of the first active frame and ends at the middle of the first inactive one."""
         F, K = discrete.shape
-        ann = Annotation(uri=uri)
-
-        def mid(i):
-            # middle of frame i = half the sum of its two ends: this order of operations decides the third decimal of
-            # the RTTM times (pinned by tests/golden/glue_*.npz, produced by the reference's Binarize)
-            s = i * FRAME_STEP
-            return 0.5 * (s + (s + FRAME_DURATION))
-        for k in range(K):
-            y = discrete[:, k].astype(np.int8)
-            if F == 0:
-                continue
-            d = np.diff(y)
-            on = list(np.where(d == 1)[0] + 1)
-            off = list(np.where(d == -1)[0] + 1)
-            if y[0] == 1:
-                on = [0] + on
-            if y[-1] == 1:
-                off = off + [F - 1]
-            for a, b in zip(on, off):
-                ann[Segment(mid(a), mid(b)), k] = k
-        return ann
+        if F == 0 or K == 0:
+            return Annotation(uri=uri)
+        y = np.zeros((F + 2, K), dtype=np.int8)
+        y[1:-1] = discrete
+        d = np.diff(y, axis=0)                       # (F + 1, K): +1 at the first active frame of a run, -1 one past its last
+        spk, first = np.nonzero(d.T == 1)            # row-major over (speaker, frame): the runs of one speaker in time order
+        _, past = np.nonzero(d.T == -1)              # ... and the frame after each of those runs, in the same order
+        last_excl = np.minimum(past, F - 1)          # a run reaching the end is closed at the last frame's middle
+        s0 = first * FRAME_STEP
+        e0 = last_excl * FRAME_STEP
+        # middle of frame i = half the sum of its two ends: this order of operations decides the third decimal of the
+        # RTTM times (pinned by tests/golden/glue_*.npz, produced by the reference's Binarize)
+        return Annotation.from_arrays(0.5 * (s0 + (s0 + FRAME_DURATION)), 0.5 * (e0 + (e0 + FRAME_DURATION)), spk, uri=uri)
 
     def __call__(self, in_wav, sess_name=None, shard: Optional[bool] = None):
         wav = load_waveform(in_wav)

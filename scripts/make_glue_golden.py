@@ -66,6 +66,41 @@ def e2e(arch_name, dur, seconds, seed, mcs):
     print(arch_name, cap["segmentations"].shape, "K =", cap["discrete"].shape[1], len(cap["turns"]), "turns")
 
 
+def e2e_large(seconds=300.0, seed=7):
+    """The BENCHMARKED architecture end to end through the reference's __call__: wavlm_large_s80_md, 16 s windows, a 5-min
+    integer-synthetic recording (tests/synth_audio.py - regenerated bit-exactly by the test, not stored), embedding bias
+    centred so that several clusters form.  Stores the oracle top-2 log-prob margin per window frame so that the GPU test
+    can explain any flipped decision without re-running the CPU oracle."""
+    import hashlib
+    from synth_audio import integer_meeting
+    from oracle.emb_oracle import emb_forward
+    from oracle.seg_oracle import seg_forward
+    a = get_arch("wavlm_large_s80_md")
+    sd = init_state_dict(a, 2, 40.0)
+    esd = init_resnet_state_dict(2)
+    w16 = integer_meeting(seconds, seed)
+    wav = w16.astype(np.float32) / 32768.0
+    # centre the embeddings on 16 calibration windows (all-ones masks)
+    N = 256000
+    cal = torch.from_numpy(np.stack([wav[s:s + N] for s in np.linspace(0, len(wav) - N - 1, 16).astype(int)]))
+    mean = emb_forward(esd, cal, torch.ones(16, 1, 799))[:, 0].mean(0)
+    esd = dict(esd)
+    esd["resnet.seg_1.bias"] = esd["resnet.seg_1.bias"] - mean
+    margins = []
+
+    def seg_fn(w):
+        logp = seg_forward(a, sd, torch.as_tensor(w))
+        t2 = logp.topk(2, dim=-1).values
+        margins.append((t2[..., 0] - t2[..., 1]).numpy())
+        return logp
+    pipe = ref_glue.build_reference_pipeline(a, sd, esd, seg_duration=16.0, min_cluster_size=10, seg_fn=seg_fn, batch_size=8)
+    cap = ref_glue.run_reference_pipeline(pipe, wav)
+    np.savez_compressed(os.path.join(OUT, "glue_e2e_large_s80.npz"), seconds=seconds, audio_seed=seed, audio_sha1=np.array(hashlib.sha1(w16.tobytes()).hexdigest()),
+                        seg_duration=16.0, weights_seed=2, classifier_gain=40.0, min_cluster_size=10,
+                        emb_bias=esd["resnet.seg_1.bias"].numpy(), margin=np.concatenate(margins).astype(np.float32), **pack(cap))
+    print("large_s80", cap["segmentations"].shape, "K =", cap["discrete"].shape[1], "clusters", int(cap["hard_clusters"].max()) + 1, len(cap["turns"]), "turns")
+
+
 # ------------------------------------------------------------------------------------------------------------
 POWERSET = [(), (0,), (1,), (2,), (3,), (0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]   # pa/utils/powerset.py:68-90 order
 
@@ -232,6 +267,8 @@ def main():
                         vbx=dict(ahc_criterion="distance", Fa=0.07, Fb=0.8, lda_dim=128, max_iters=20)),
         }, seed=10)
         synth("16s", 16.0, 187.9, [0.8, 0.6, 0.5, 0.08], {"default": dict(V, min_cluster_size=4)}, seed=20)
+    if "large" in which:
+        e2e_large()
     if "e2e" in which:
         e2e("tiny_base", 5.0, 31.3, 1, 3)
         e2e("tiny_large", 16.0, 61.0, 4, 2)

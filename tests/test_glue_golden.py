@@ -36,6 +36,21 @@ def test_e2e_golden(arch):
     assert po.to_rttm(out["turns"], "sess") == str(z["rttm"])
 
 
+def test_e2e_large_s80_golden():
+    """the 5-minute wavlm_large_s80_md golden: oracle glue on the stored window decisions / embeddings == the reference's output;
+    also checks that the integer-synthetic recording is regenerated bit-exactly on this machine"""
+    import hashlib
+    from synth_audio import integer_meeting
+    z = np.load(os.path.join(G, "glue_e2e_large_s80.npz"))
+    w16 = integer_meeting(float(z["seconds"]), int(z["audio_seed"]))
+    assert hashlib.sha1(w16.tobytes()).hexdigest() == str(z["audio_sha1"])
+    seg_fn, emb_fn = _feed(z)
+    out = po.run_pipeline(w16.astype(np.float32) / 32768.0, seg_fn, emb_fn, 16.0, 0.1, threshold=0.70, min_cluster_size=int(z["min_cluster_size"]),
+                          min_speakers=1, max_speakers=20)
+    assert np.array_equal(out["segmentations"], z["segmentations"]) and np.array_equal(out["hard_clusters"], z["hard_clusters"])
+    assert np.array_equal(out["discrete"], z["discrete"]) and po.to_rttm(out["turns"], "sess") == str(z["rttm"])
+
+
 def _synth_cases():
     out = []
     for name in ("5s", "16s"):
