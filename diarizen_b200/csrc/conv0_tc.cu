@@ -177,6 +177,15 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_kernel(const Conv0Arg
           tmem_ld_32x32(tmem_base + lane_off + (uint32_t)c0, r);
           tmem_ld_wait();
           const int nv = NP - c0;   // columns >= NP were never written
+          if (nv >= 32) {           // whole chunk valid (every chunk when C0 is a multiple of 32): no per-element predicates
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              s0 += __uint_as_float(r[c]); s1 += __uint_as_float(r[c + 1]); s2 += __uint_as_float(r[c + 2]); s3 += __uint_as_float(r[c + 3]);
+            }
+            s += (s0 + s1) + (s2 + s3);
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 32; ++c) s += (c < nv) ? __uint_as_float(r[c]) : 0.f;   // channels C0..NP-1 are exact zeros
         }
@@ -192,6 +201,17 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_kernel(const Conv0Arg
           tmem_ld_32x32(tmem_base + lane_off + (uint32_t)c0, r);
           tmem_ld_wait();
           const int nv = C0 - c0;
+          if (nv >= 32) {
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float d0 = __uint_as_float(r[c]) - mean, d1 = __uint_as_float(r[c + 1]) - mean;
+              const float d2 = __uint_as_float(r[c + 2]) - mean, d3 = __uint_as_float(r[c + 3]) - mean;
+              q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+            }
+            q += (q0 + q1) + (q2 + q3);
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 32; ++c) { const float dl = __uint_as_float(r[c]) - mean; q = (c < nv) ? fmaf(dl, dl, q) : q; }
         }
@@ -215,6 +235,22 @@ __global__ void __launch_bounds__(C0T_THREADS, 1) conv0_tc_kernel(const Conv0Arg
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c) r[c] = 0u;
+          }
+          if (c0 + 32 <= C0) {
+            // whole chunk inside the channel range: straight-line code, no per-element predicates or branches around the GELU
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 g = *reinterpret_cast<const float4*>(cf + 2 * (c0 + 8 * c8 + 2 * e));
+                float y0 = __uint_as_float(r[8 * c8 + 2 * e]), y1 = __uint_as_float(r[8 * c8 + 2 * e + 1]);
+                if (LARGE) { y0 = fmaf(y0, sc, of); y1 = fmaf(y1, sc, of); }
+                w4[e] = pack2_16<1>(gelu_erf(fmaf(y0, g.x, g.y)), gelu_erf(fmaf(y1, g.z, g.w)));
+              }
+              if (rvalid) *reinterpret_cast<uint4*>(orow + c0 + 8 * c8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            continue;
           }
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {

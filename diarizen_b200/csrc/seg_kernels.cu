@@ -821,8 +821,8 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(DwArgs a) {
     }
   }
 }
-// v2 (opt-in, DZ_DWCONV_V2=1, until compared on hardware; the accumulation order per output is the same as above, so the
-// results must be bit-identical): 64 frames per CTA (halo overhead 1.47x instead of 1.94x) and four outputs per thread in
+// v2 (default; DZ_DWCONV_V1=1 selects the kernel above): same accumulation order per output, fast-intrinsic sigmoids (ncu of
+// the IEEE-division version: 264 instructions per output, most of them the two sigmoids); 64 frames per CTA (halo overhead 1.47x instead of 1.94x) and four outputs per thread in
 // flight, which share every shared-memory load (0.27 LDS per FMA instead of 1) and break the dependent FMA chain.
 static constexpr int DW2_TT = 64;
 __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
       float v = 0.f;
       if (in) {
         const float g = xr[A + c];
-        v = xr[c] / (1.f + expf(-g));
+        v = __fdividef(xr[c], 1.f + __expf(-g));      // GLU gate; same fast sigmoid as the GEMM epilogue's swish
       }
       smd[r * A + c] = v;
     }
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
         const int tq = t0 + tt + u;
         if (tq < a.T) {
           float y = acc[u] * sc + sh;
-          y = y / (1.f + expf(-y));
+          y = __fdividef(y, 1.f + __expf(-y));
           bf16 h, l;
           split_bf16(y, h, l, a.fp16);
           const long long o = ((long long)b * a.T + tq) * a.ldo + c;
