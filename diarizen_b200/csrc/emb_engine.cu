@@ -44,6 +44,7 @@ struct dz_emb {
   std::vector<Step> steps;
   std::vector<GemmPlan*> plans;
   std::vector<Conv3Plan*> c3plans;
+  std::vector<ConvSPlan*> csplans;
   std::vector<DevMem*> ws;
   DevMem widx;
   const float* cur_wav = nullptr; const float* cur_masks = nullptr; float* cur_out = nullptr;
@@ -56,6 +57,8 @@ struct dz_emb {
     plans.clear();
     for (auto* p : c3plans) conv3x3_c32_plan_destroy(p);
     c3plans.clear();
+    for (auto* p : csplans) conv3x3_stream_plan_destroy(p);
+    csplans.clear();
     for (auto* w : ws) delete w;
     ws.clear();
     steps.clear();
@@ -272,6 +275,18 @@ static int emb_plan(dz_emb* s, int B, int N, int S, int T) {
       s->steps.push_back({nm, [cp](cudaStream_t st) { return conv3x3_c32_plan_launch(cp, st); }, flops, 0.0});
       return;
     }
+    static const bool c128_off = [] { const char* e = getenv("DZ_CONV128_GENERIC"); return e && e[0] == '1'; }();
+    if (!c128_off && ks == 3 && stride == 1 && Cin == Cout && Cin == 128 && P == 1 && s->npass == 1 && act == 3) {
+      // layer3: streamed weights, two output rows per tile, row-shifted A views (conv3x3_c128.cu)
+      Conv3Args c{};
+      c.in = in.p; c.out = out.p; c.res = res ? res->p : nullptr; c.w = W.w.as<bf16>(); c.ldw = W.ldb; c.bias = W.bias.as<float>();
+      c.B = B; c.H = Hin; c.W = Win; c.relu = 1; c.fp16 = FP; c.C = Cin;
+      ConvSPlan* cp = conv3x3_stream_plan_create(c);
+      if (!cp) { if (!err) { err = DZ_ERR_CUDA; msg = "conv3x3 stream plan '" + nm + "': " + gemm_last_error(); } return; }
+      s->csplans.push_back(cp);
+      s->steps.push_back({nm, [cp](cudaStream_t st) { return conv3x3_stream_plan_launch(cp, st); }, flops, 0.0});
+      return;
+    }
     GemmPlan* p = gemm_plan_create(d, 0);
     if (!p) { if (!err) { err = DZ_ERR_CUDA; msg = "gemm plan '" + nm + "': " + gemm_last_error(); } return; }
     s->plans.push_back(p);
@@ -436,3 +451,30 @@ int dz_emb_profile(dz_emb* s, float* ms_out, double* flops_out, char* names, int
 }
 
 }  // extern "C"
+
+extern "C" int dz_conv3x3(const void* in_dev, void* out_dev, const void* res_dev, const void* w_dev, int ldw, const float* bias_dev, int B,
+                          int H, int W, int C, int relu, int fp16, void* stream) {
+  using namespace dz;
+  if (!in_dev || !out_dev || !w_dev || B < 1 || H < 1 || W < 1) return fail(DZ_ERR_INVALID, "bad argument");
+  Conv3Args c{};
+  c.in = (const bf16*)in_dev; c.out = (bf16*)out_dev; c.res = (const bf16*)res_dev; c.w = (const bf16*)w_dev; c.ldw = ldw; c.bias = bias_dev;
+  c.B = B; c.H = H; c.W = W; c.relu = relu; c.fp16 = fp16; c.C = C;
+  cudaError_t e;
+  if (C == 128) {
+    ConvSPlan* p = conv3x3_stream_plan_create(c);
+    if (!p) return fail(DZ_ERR_CUDA, std::string("conv3x3 plan: ") + gemm_last_error());
+    e = conv3x3_stream_plan_launch(p, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    conv3x3_stream_plan_destroy(p);
+  } else if (C == 32 || C == 64) {
+    Conv3Plan* p = conv3x3_c32_plan_create(c);
+    if (!p) return fail(DZ_ERR_CUDA, std::string("conv3x3 plan: ") + gemm_last_error());
+    e = conv3x3_c32_plan_launch(p, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    conv3x3_c32_plan_destroy(p);
+  } else {
+    return fail(DZ_ERR_INVALID, "dz_conv3x3: C must be 32, 64 or 128");
+  }
+  if (e != cudaSuccess) return fail(DZ_ERR_CUDA, cudaGetErrorString(e));
+  return DZ_OK;
+}

@@ -43,6 +43,11 @@ struct Conv3Plan;
 Conv3Plan* conv3x3_c32_plan_create(const Conv3Args& a);
 void conv3x3_c32_plan_destroy(Conv3Plan* p);
 cudaError_t conv3x3_c32_plan_launch(const Conv3Plan* p, cudaStream_t st);
+// same contract for C = 128 (layer3) with streamed weights and two output rows per tile (conv3x3_c128.cu)
+struct ConvSPlan;
+ConvSPlan* conv3x3_stream_plan_create(const Conv3Args& a);
+void conv3x3_stream_plan_destroy(ConvSPlan* p);
+cudaError_t conv3x3_stream_plan_launch(const ConvSPlan* p, cudaStream_t st);
 cudaError_t launch_zero_borders(__nv_bfloat16* p, long long plane, int planes, long long rows, int W, int C, cudaStream_t st);
 
 }  // namespace dz

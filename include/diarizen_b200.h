@@ -198,6 +198,11 @@ int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream);
 /* scipy linkage(method="centroid") from the distance matrix (destroyed); Z [N-1][4] float64 */
 int64_t dz_linkage_workspace_bytes(int N);
 int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream);
+/* Unit-test surface of the stride-1 3x3 convolution kernels of the embedding trunk (conv3x3_c32.cu: C = 32 / 64 with resident
+ * weights; conv3x3_c128.cu: C = 128 with streamed weights).  in / out / res: zero-bordered NHWC 16-bit planes [B][H][W+2][C];
+ * w: [C][ldw] with element (kh, kw, ci) at kh * rup(3C, 64) + kw * C + ci; out = relu(conv(in) + bias + res). */
+int dz_conv3x3(const void* in_dev, void* out_dev, const void* res_dev, const void* w_dev, int ldw, const float* bias_dev, int B, int H,
+               int W, int C, int relu, int fp16, void* stream);
 /* Flat clusters from the dendrogram of dz_linkage_centroid, selected as AgglomerativeClustering.cluster selects them
  * (pyannote-audio/pyannote/audio/pipelines/clustering.py:418-492): cut at `threshold` (scipy fcluster, criterion "distance");
  * when the number of clusters with >= min_cluster_size members falls outside [min_clusters, max_clusters] (or differs from

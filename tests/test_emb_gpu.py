@@ -62,3 +62,39 @@ def test_reference_call_convention():
     m = EmbeddingModel(sd, precision="bf16x3")
     out = m(wav[:, None, :], masks=masks[:, 0])
     assert out.shape == (2, 256) and out.dtype.name == "float32"
+
+
+@pytest.mark.parametrize("C,B,H,W", [(128, 2, 20, 400), (128, 3, 7, 133), (128, 1, 1, 16), (64, 2, 40, 300), (32, 2, 9, 131)])
+@pytest.mark.parametrize("fp16", [1, 0])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_conv3x3_kernels_vs_torch(C, B, H, W, fp16, with_res):
+    """The stride-1 3x3 convolution kernels of the ResNet trunk (resident-weight kernel for C = 32 / 64, streamed-weight
+    two-row kernel for C = 128: odd H, a ragged last pixel tile and a single-row image included) against torch.conv2d in
+    float64 on the same 16-bit-rounded operands."""
+    import ctypes as C_
+    from diarizen_b200 import _lib
+    g = torch.Generator().manual_seed(C + H + W)
+    dt = torch.float16 if fp16 else torch.bfloat16
+    x = torch.randn(B, H, W, C, generator=g).to(dt)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(dt)      # [out][in][kh][kw]
+    bias = torch.randn(C, generator=g)
+    res = torch.randn(B, H, W, C, generator=g).to(dt)
+    krun = (3 * C + 63) // 64 * 64
+    ldw = 3 * krun
+    wl = torch.zeros(C, 3, krun, dtype=dt)
+    wl[:, :, :3 * C] = w.permute(0, 2, 3, 1).reshape(C, 3, 3 * C)           # (kh, kw, ci) at kh * krun + kw * C + ci
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 1, 1)).contiguous().cuda()   # zero border columns
+    xin, rin = pad(x), pad(res)
+    out = torch.full((B, H, W + 2, C), 7.0, dtype=dt, device="cuda")
+    wd, bd = wl.reshape(C, ldw).contiguous().cuda(), bias.cuda()
+    vp = C_.c_void_p
+    _lib.check(_lib.lib().dz_conv3x3(vp(xin.data_ptr()), vp(out.data_ptr()), vp(rin.data_ptr()) if with_res else None, vp(wd.data_ptr()), ldw,
+                                     vp(bd.data_ptr()), B, H, W, C, 1, fp16, None))
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    if with_res:
+        ref = ref + res.double()
+    ref = torch.relu(ref)
+    got = out[:, :, 1:W + 1].double().cpu()
+    err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+    assert err < (1.5e-3 if fp16 else 1e-2), f"rel err {err:.3e}"           # output rounding of the 16-bit format dominates
+    assert (out[:, :, 0] == 7.0).all() and (out[:, :, W + 1] == 7.0).all(), "border columns must not be written"
