@@ -132,9 +132,9 @@ def test_reconstruct_many_clusters():
         cnt = np.minimum(count_ref, 3).astype(np.int8)
         ref = po.reconstruct(segf, hard, cnt, dur, step)
         dd = torch.empty((F, K), dtype=torch.uint8, device="cuda")
-        _lib.check(_lib.lib().dz_reconstruct(vp(torch.as_tensor(seg, device="cuda").data_ptr()), vp(torch.as_tensor(hard, device="cuda").data_ptr()),
-                                             vp(torch.as_tensor(start, device="cuda").data_ptr()),
-                                             vp(torch.as_tensor(cnt[:, 0].astype(np.uint8), device="cuda").data_ptr()), Cn, T, S, K, K, F,
+        dseg, dh, dst = torch.as_tensor(seg, device="cuda"), torch.as_tensor(hard, device="cuda"), torch.as_tensor(start, device="cuda")
+        dc = torch.as_tensor(cnt[:, 0].astype(np.uint8), device="cuda")      # keep the device tensors alive across the launch
+        _lib.check(_lib.lib().dz_reconstruct(vp(dseg.data_ptr()), vp(dh.data_ptr()), vp(dst.data_ptr()), vp(dc.data_ptr()), Cn, T, S, K, K, F,
                                              vp(dd.data_ptr()), None, None))
         assert np.array_equal(dd.cpu().numpy().astype(np.float64), ref), K
 
