@@ -11,6 +11,7 @@
 
 #include "../../include/diarizen_b200.h"
 #include "common.cuh"
+#include "lsap_small.cuh"
 
 namespace dz {
 std::string& tls_error();
@@ -445,95 +446,16 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel_v2(double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Constrained assignment (one distinct cluster per local speaker, maximise the summed score): exhaustive search over
-// the S! / (S - min(S,K))! ... injective maps, S <= 4, K <= 32.  One thread per chunk.
-// reference: clustering.py:159-173 (scipy.optimize.linear_sum_assignment(maximize=True) per chunk).
+// Constrained assignment (one distinct cluster per local speaker, maximal total score; clustering.py:159-173): one thread per
+// chunk runs the shortest-augmenting-path solver of lsap_small.cuh - scipy's algorithm step for step, so that the many exact
+// ties (inactive local speakers share one embedding, hence identical score rows) resolve exactly as in the reference.
 // ------------------------------------------------------------------------------------------------
-__global__ void assign_kernel(const double* __restrict__ soft, int C, int S, int K, int8_t* __restrict__ hard) {
+__global__ void __launch_bounds__(64) assign_kernel(const double* __restrict__ soft, int C, int S, int K, int8_t* __restrict__ hard) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double* sc = soft + (long long)c * S * K;
-  const int m = min(S, K);      // pairs to assign
-  int best[4] = {-2, -2, -2, -2};
-  double bestv = -INFINITY;
-  int a[4];
-  // enumerate a[s] in {-1 (unassigned), 0..K-1}, distinct clusters, exactly m assigned
-  const int base = K + 1;
-  int total = 1;
-  for (int s = 0; s < S; ++s) total *= base;
-  for (int code = 0; code < total; ++code) {
-    int t = code, assigned = 0;
-    unsigned used = 0;
-    bool ok = true;
-    double v = 0.0;
-    // speaker 0 is the most significant digit: among equal totals the lexicographically smallest map wins, which is what
-    // scipy's solver returns for the all-equal (NaN-filled) rows of inactive speakers
-    for (int s = S - 1; s >= 0; --s) {
-      const int dgt = t % base;
-      const int k = dgt < K ? dgt : -1;     // "unassigned" sorts after every cluster
-      t /= base;
-      a[s] = k;
-      if (k >= 0) {
-        if ((used >> k) & 1u) { ok = false; break; }
-        used |= 1u << k;
-        ++assigned;
-        v += sc[s * K + k];
-      }
-    }
-    if (!ok || assigned != m) continue;
-    if (v > bestv) { bestv = v; for (int s = 0; s < S; ++s) best[s] = a[s] >= 0 ? a[s] : -2; }
-  }
-  for (int s = 0; s < S; ++s) hard[c * S + s] = (int8_t)best[s];
-}
-
-// K >= S: every local speaker gets a cluster, and some optimal map gives each speaker one of its S best clusters (at
-// most S - 1 of them can be taken by the others), so the search runs over S candidates per speaker (<= 256 maps) whatever K.
-// Candidates are ranked by (score descending, cluster index ascending); among equal totals the lexicographically smallest
-// map wins, as in assign_kernel.
-__global__ void assign_topk_kernel(const double* __restrict__ soft, int C, int S, int K, int8_t* __restrict__ hard) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double* sc = soft + (long long)c * S * K;
-  int cand[4][4];
-  double cval[4][4];
-  for (int s = 0; s < S; ++s) {
-    for (int j = 0; j < S; ++j) {
-      int bk = -1; double bv = -INFINITY;
-      for (int k = 0; k < K; ++k) {
-        bool taken = false;
-        for (int q = 0; q < j; ++q) taken |= cand[s][q] == k;
-        if (taken) continue;
-        const double v = sc[s * K + k];
-        if (bk < 0 || v > bv) { bv = v; bk = k; }
-      }
-      cand[s][j] = bk; cval[s][j] = bv;
-    }
-  }
-  int best[4] = {-2, -2, -2, -2};
-  double bestv = -INFINITY;
-  int total = 1;
-  for (int s = 0; s < S; ++s) total *= S;
-  for (int code = 0; code < total; ++code) {
-    int a[4] = {-1, -1, -1, -1};
-    int t = code;
-    double v = 0.0;
-    bool ok = true;
-    for (int s = 0; s < S && ok; ++s) {
-      const int j = t % S; t /= S;
-      a[s] = cand[s][j];
-      for (int q = 0; q < s; ++q) ok &= a[q] != a[s];
-      v += cval[s][j];
-    }
-    if (!ok) continue;
-    bool better = v > bestv;
-    if (!better && v == bestv) {
-      for (int s = 0; s < S; ++s) {
-        if (a[s] != best[s]) { better = a[s] < best[s]; break; }
-      }
-    }
-    if (better) { bestv = v; for (int s = 0; s < S; ++s) best[s] = a[s]; }
-  }
-  for (int s = 0; s < S; ++s) hard[c * S + s] = (int8_t)best[s];
+  int8_t h[4];
+  lsap_assign_max(soft + (long long)c * S * K, S, K, h);
+  for (int s = 0; s < S; ++s) hard[c * S + s] = h[s];
 }
 
 }  // namespace dz
@@ -620,8 +542,7 @@ int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_
 }
 int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream) {
   if (!soft_dev || !hard_dev || S < 1 || S > 4 || K < 1 || K > 127) return fail(DZ_ERR_INVALID, "bad argument (S <= 4, K <= 127: labels are int8)");
-  if (K < S || K <= 4) assign_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
-  else assign_topk_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
+  assign_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(soft_dev, C, S, K, hard_dev);
   CK_LAUNCH();
   return DZ_OK;
 }

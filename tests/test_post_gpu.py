@@ -103,10 +103,18 @@ def test_linkage_matches_scipy_bitwise(n, seed):
 
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 7, 12, 31, 40, 127])
 def test_assign_matches_hungarian(K):
+    """dz_assign == scipy.optimize.linear_sum_assignment(maximize=True) per chunk, INCLUDING the tie patterns of the pipeline:
+    identical rows (inactive local speakers share one embedding) and constant rows (NaN scores -> global minimum)."""
     from scipy.optimize import linear_sum_assignment
     from diarizen_b200.clustering import device_assign
     rng = np.random.default_rng(K)
-    soft = 2 - rng.random((200, 4, K)) * 2
+    n = 240
+    soft = 2 - rng.random((n, 4, K)) * 2
+    for c in range(0, n, 4):
+        soft[c, rng.integers(1, 4)] = soft[c, 0]
+    for c in range(1, n, 4):
+        soft[c, rng.choice(4, size=int(rng.integers(1, 5)), replace=False)] = soft[c].min()
+    soft[2::8] = np.round(soft[2::8] * 3) / 3
     hard = device_assign(soft)
     for c in range(soft.shape[0]):
         ref = -2 * np.ones(4, dtype=np.int8)
