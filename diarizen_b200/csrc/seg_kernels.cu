@@ -825,9 +825,10 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(DwArgs a) {
 // the IEEE-division version: 264 instructions per output, most of them the two sigmoids); 64 frames per CTA (halo overhead 1.47x instead of 1.94x) and four outputs per thread in
 // flight, which share every shared-memory load (0.27 LDS per FMA instead of 1) and break the dependent FMA chain.
 static constexpr int DW2_TT = 64;
+template <int KS>   // KS > 0: kernel size known at compile time (31 in every shipped configuration) - no per-tap predicates
 __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
   extern __shared__ float smd[];  // [(TT + k - 1)][A]
-  const int A = a.A, K = a.ksize, half = (K - 1) / 2;
+  const int A = a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
   const int b = blockIdx.y, t0 = blockIdx.x * DW2_TT;
   const int nrow = DW2_TT + K - 1;
   for (int r = 0; r < nrow; ++r) {
@@ -888,11 +889,13 @@ cudaError_t launch_glu_dwconv(const DwArgs& a, int B, cudaStream_t st) {
     if (smem2 <= 200 * 1024) {
       static size_t attr2 = 0;
       if (smem2 > 48 * 1024 && smem2 > attr2) {
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         attr2 = smem2;
       }
       dim3 grid2((a.T + DW2_TT - 1) / DW2_TT, B);
-      glu_dwconv_v2_kernel<<<grid2, 256, smem2, st>>>(a);
+      if (a.ksize == 31) glu_dwconv_v2_kernel<31><<<grid2, 256, smem2, st>>>(a);
+      else glu_dwconv_v2_kernel<0><<<grid2, 256, smem2, st>>>(a);
       return cudaGetLastError();
     }
   }

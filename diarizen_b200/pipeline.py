@@ -30,7 +30,7 @@ from .archs import SegArch, arch_from_reference_config, get_arch, init_state_dic
 from .clustering import AgglomerativeClustering, VBxClustering
 from .embedding import EmbeddingModel
 from .segmentation import SegmentationModel
-from .sharding import gather_records, window_range
+from .sharding import gather_records, window_ranges
 
 SR = 16000
 FRAME_DURATION = 400 / SR    # receptive field of the conv stack (model_wavlm_conformer.py:126-176)
@@ -200,6 +200,9 @@ class DiariZenPipeline:
         self.rttm_out_dir = rttm_out_dir
         self._L = _lib.lib()
         self.last = {}
+        # window-sharded mode: fraction of an even window share that the clustering rank takes (None = even split); see
+        # sharding.window_ranges.  DZ_ROOT_SHARE overrides.
+        self.root_share = float(os.environ["DZ_ROOT_SHARE"]) if os.environ.get("DZ_ROOT_SHARE") else None
         self.collect_timing = os.environ.get("DZ_TIMING") is not None
         self._timing, self._t_last = {}, None
 
@@ -399,7 +402,8 @@ class DiariZenPipeline:
             Nw = wav.shape[0]
             window, step, Cn = self._windows(Nw)
             T = self._segmentation.num_frames(window)
-            c0, c1, per = window_range(Cn, rank, world)
+            ranges, per = window_ranges(Cn, world, root, self.root_share if world > 1 else None)
+            c0, c1 = ranges[rank]
             # this rank's span of the recording: windows c0..c1-1 (zero padded past the end for the orphan chunk)
             s0, s1 = c0 * step, (max(c1, c0 + 1) - 1) * step + window
             if wav.device == dev and wav.dtype == torch.float32 and Nw >= s1:
@@ -412,13 +416,41 @@ class DiariZenPipeline:
             raw, seg, stats, emb = self._front(wloc, c1 - c0, window, step, T, c0, c1, per)
             self.last_raw = raw[:c1 - c0]      # this rank's window decisions before the median filter (parity tests)
             if world > 1:
-                seg, stats, emb = gather_records(seg, stats, emb, Cn, world)
+                seg, stats, emb = gather_records(seg, stats, emb, Cn, world, ranges)
                 self._mark("all_gather")
                 if rank != root:
                     return {}
             else:
                 seg, stats, emb = seg[:Cn], stats[:Cn], emb[:Cn]
             return self._back(seg, stats, emb, Cn, T)
+
+    def tune_root_share(self, wav: torch.Tensor, root: int = 0) -> Optional[float]:
+        """Window-sharded mode, recordings processed back to back: measure one sharded pass with stage timers and give the
+        clustering rank the window share at which its networks + clustering take as long as the other ranks' networks
+        (w_root = w_other - tail / t_window).  Collective: call on every rank.  -> the share (also stored in `root_share`)."""
+        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        if dist is None or dist.get_world_size() < 2:
+            return None
+        world, rank = dist.get_world_size(), dist.get_rank()
+        keep, self.collect_timing, self.root_share = self.collect_timing, True, None
+        import time
+        res = self.diarize_waveform(wav, shard=True, root=root)
+        t0 = time.perf_counter()
+        if res:
+            self.to_annotation(res["discrete"], None)
+        share = torch.zeros(1, device=self.device, dtype=torch.float64)
+        if rank == root:
+            tm = res["timing"]
+            Cn = res["num_chunks"]
+            n_root = -(-Cn // world)
+            t_window = (tm.get("segmentation", 0.0) + tm.get("count_masks", 0.0) + tm.get("embedding", 0.0)) / max(1, n_root)
+            tail = tm.get("gather_to_host", 0.0) + tm.get("clustering", 0.0) + tm.get("reconstruct", 0.0) + 1e3 * (time.perf_counter() - t0)
+            w_other = (Cn + tail / max(t_window, 1e-6)) / world
+            share[0] = min(1.0, max(0.05, (w_other - tail / max(t_window, 1e-6)) / (Cn / world)))
+        dist.all_reduce(share)
+        self.collect_timing = keep
+        self.root_share = float(share.item())
+        return self.root_share
 
     def diarize_segmentations(self, raw_segmentations, embeddings) -> Dict[str, Any]:
         """Stage 2 alone: (C,T,4) {0,1} window decisions as they leave the segmentation network and (C,4,256) embeddings ->

@@ -13,6 +13,27 @@ def window_range(num_windows: int, rank: int, world: int) -> Tuple[int, int, int
     return min(rank * per, num_windows), min((rank + 1) * per, num_windows), per
 
 
+def window_ranges(num_windows: int, world: int, root: int = 0, root_share: float = None):
+    """-> ([(first, one-past-last)] per rank, rows per rank incl. padding).  `root_share` in (0, 1]: the rank that also
+    clusters (`root`) takes that fraction of an even share and the others split the rest, so that - with recordings processed
+    back to back - its networks + clustering take as long as the other ranks' networks alone."""
+    if world == 1 or not root_share or root_share >= 1.0:
+        per = (num_windows + world - 1) // world
+        return [(min(r * per, num_windows), min((r + 1) * per, num_windows)) for r in range(world)], per
+    n_root = max(0, min(num_windows, int(round(root_share * num_windows / world))))
+    rest = num_windows - n_root
+    others = world - 1
+    base, extra = divmod(rest, others)
+    out, pos, k = [], 0, 0
+    for r in range(world):
+        n = n_root if r == root else base + (1 if k < extra else 0)
+        if r != root:
+            k += 1
+        out.append((pos, pos + n))
+        pos += n
+    return out, max(1, max(b - a for a, b in out))
+
+
 def gather_windows(local: torch.Tensor, num_windows: int, world: int) -> torch.Tensor:
     """local: (per, ...) this rank's (zero padded) slice -> (num_windows, ...) on every rank.  One collective."""
     if world == 1:
@@ -54,8 +75,18 @@ def unpack_records(buf: torch.Tensor, seg_shape, stats_shape, emb_shape):
     return seg, stats, emb
 
 
-def gather_records(seg: torch.Tensor, stats: torch.Tensor, emb: torch.Tensor, num_windows: int, world: int):
+def gather_records(seg: torch.Tensor, stats: torch.Tensor, emb: torch.Tensor, num_windows: int, world: int, ranges=None):
     """The single data-path collective of the window-sharded mode: every rank contributes its packed per-window records
-    (binarised segmentations, frame counters, embeddings); -> the three tensors for all `num_windows` windows."""
-    buf = gather_windows(pack_records(seg, stats, emb), num_windows, world)
+    (binarised segmentations, frame counters, embeddings); -> the three tensors for all `num_windows` windows.
+    `ranges`: per-rank (first, one-past-last) when the split is uneven (window_ranges with a root share); every rank still
+    sends the same number of (padded) rows, and the valid prefix of each rank's block is kept."""
+    packed = pack_records(seg, stats, emb)
+    if ranges is None or world == 1:
+        buf = gather_windows(packed, num_windows, world)
+    else:
+        import torch.distributed as dist
+        per = packed.shape[0]
+        full = torch.empty((world * per, packed.shape[1]), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(full, packed.contiguous())
+        buf = torch.cat([full[r * per:r * per + (b - a)] for r, (a, b) in enumerate(ranges)])
     return unpack_records(buf, seg.shape[1:], stats.shape[1:], emb.shape[1:])

@@ -93,7 +93,7 @@ def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from diarizen_b200.sharding import gather_windows, window_range
+    from diarizen_b200.sharding import gather_windows, window_range, window_ranges
     Cn, T = 11, 7
     a, b, per = window_range(Cn, rank, world)
     local = torch.zeros((per, T), dtype=torch.uint8)
@@ -114,6 +114,14 @@ def _shard_worker(rank, world, port, q):
     dist.all_gather_into_tensor = lambda *a_, **k_: (calls.append(1), orig(*a_, **k_))[1]
     g = gather_records(seg, stats, emb, Cn, world)
     dist.all_gather_into_tensor = orig
+    # uneven split: the clustering rank (root 1 here) takes 40 % of an even share
+    rg, per_u = window_ranges(Cn, world, root=1, root_share=0.4)
+    ua, ub = rg[rank]
+    seg_u = torch.zeros((per_u, T, 4), dtype=torch.uint8); st_u = torch.zeros((per_u, 4, 2), dtype=torch.int32); em_u = torch.zeros((per_u, 4, 5))
+    for c in range(ua, ub):
+        em_u[c - ua] = c + 0.5
+    gu = gather_records(seg_u, st_u, em_u, Cn, world, rg)
+    uneven_ok = rg == [(0, 9), (9, 11)] and per_u == 9 and all(float(gu[2][c, 0, 0]) == c + 0.5 for c in range(Cn)) and gu[0].shape[0] == Cn
     ok = (len(calls) == 1 and g[0].shape == (Cn, T, 4) and g[1].dtype == torch.int32 and g[2].dtype == torch.float32
           and all(int(g[0][c].max()) == c % 2 and int(g[1][c, 3, 1]) == 1000 * c + 7 and float(g[2][c, 0, 0]) == c + 0.25 for c in range(Cn)))
     # dispatch policy for several recordings (diarize_many): whole recordings round-robin, the remainder window-sharded with a rotating root
@@ -129,7 +137,7 @@ def _shard_worker(rank, world, port, q):
             return {"discrete": np.zeros((3, 1), dtype=np.uint8)} if (shard is False or rank == root) else {}
 
     outs = Fake().diarize_many([torch.full((4,), float(i)) for i in range(5)], [f"r{i}" for i in range(5)])
-    q.put((rank, full.numpy(), ok, log, [o is not None for o in outs]))
+    q.put((rank, full.numpy(), ok and uneven_ok, log, [o is not None for o in outs]))
     dist.destroy_process_group()
 
 
