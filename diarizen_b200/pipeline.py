@@ -200,6 +200,7 @@ class DiariZenPipeline:
         self.rttm_out_dir = rttm_out_dir
         self._L = _lib.lib()
         self.last = {}
+        self._tails = {}
         # window-sharded mode: fraction of an even window share that the clustering rank takes (None = even split); see
         # sharding.window_ranges.  DZ_ROOT_SHARE overrides.
         self.root_share = float(os.environ["DZ_ROOT_SHARE"]) if os.environ.get("DZ_ROOT_SHARE") else None
@@ -215,6 +216,7 @@ class DiariZenPipeline:
         self._embedding = self._embedding.to(device)
         self.device = self._segmentation.device
         self.clustering.device = self.device
+        self._tails = {}
         return self
 
     @property
@@ -291,11 +293,15 @@ class DiariZenPipeline:
             if b - a == bs or n_loc < bs:
                 self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=raw[a:b])
             else:
-                wpad = torch.zeros((bs, window), device=dev, dtype=torch.float32)
-                wpad[:b - a] = chunks[a:b]
-                tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
-                self._segmentation.hard(wpad, want_logp=False, ml_out=tail)
-                raw[a:b] = tail[:b - a]
+                # ragged last batch: padded to a planned batch size (bs, or bs / 2 on a second engine instance that keeps its
+                # own plan) - never a re-plan of the main engine
+                rem = b - a
+                eng, pb = (self._tail_engine("seg"), bs // 2) if rem <= bs // 2 else (self._segmentation, bs)
+                wpad = torch.zeros((pb, window), device=dev, dtype=torch.float32)
+                wpad[:rem] = chunks[a:b]
+                tail = torch.empty((pb, T, S), device=dev, dtype=torch.uint8)
+                eng.hard(wpad, want_logp=False, ml_out=tail)
+                raw[a:b] = tail[:rem]
         self._mark("segmentation")
         return (raw,) + self._masks_and_embeddings(raw, wloc, chunks, window, step, T, c0, c1, per)
 
@@ -327,10 +333,15 @@ class DiariZenPipeline:
                 wv = torch.stack([torch.nn.functional.pad(wloc[max(e_starts[i], 0):e_starts[i] + window], (0, max(0, e_starts[i] + window - wloc.shape[0])))[:window]
                                   for i in range(a, b)])
             mk = masks[a:b]
-            if b - a < ebs and n_loc >= ebs:   # pad the ragged last batch (see above)
-                wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
-                mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
-            emb[a:b] = self._embedding.embed_windows(wv, mk)[:b - a]
+            eng = self._embedding
+            if b - a < ebs and n_loc >= ebs:   # ragged last batch: pad to ebs, or to ebs / 4 on a second engine instance
+                rem = b - a
+                pb = ebs
+                if rem <= ebs // 4 and ebs >= 8:
+                    eng, pb = self._tail_engine("emb"), ebs // 4
+                wv = torch.cat([wv, torch.zeros((pb - rem, window), device=dev, dtype=torch.float32)])
+                mk = torch.cat([mk, torch.zeros((pb - rem, S, T), device=dev, dtype=torch.float32)])
+            emb[a:b] = eng.embed_windows(wv, mk)[:b - a]
         self._mark("embedding")
         return seg, stats, emb
 
@@ -371,6 +382,19 @@ class DiariZenPipeline:
                "centroids": centroids, "num_chunks": Cn, "num_frames": T, "timing": dict(self._timing)}
         self.last = out
         return out
+
+    def _tail_engine(self, which: str):
+        """second instance of a network engine (same weights) that serves the small ragged last batch of a recording: each
+        instance keeps the plan of ONE batch shape, so neither ever re-plans while recordings of different lengths stream by"""
+        if which not in self._tails:
+            m = self._segmentation if which == "seg" else self._embedding
+            if which == "seg":
+                sd, gi, ai = m._ctor
+                self._tails[which] = SegmentationModel(m.arch, sd, precision=m.precision, gemm_impl=gi, attn_impl=ai, device=self.device)
+            else:
+                sd, precision, gi, prefix = m._ctor
+                self._tails[which] = EmbeddingModel(sd, precision=precision, gemm_impl=gi, device=self.device, prefix=prefix)
+        return self._tails[which]
 
     def _mark(self, name: Optional[str]):
         """stage timer (only with `collect_timing`, which synchronises the device at every stage boundary)"""
