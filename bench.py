@@ -617,6 +617,15 @@ def emit(obj) -> None:
 
 
 def main():
+    # the ONE JSON line owns the real stdout: keep a private duplicate of file descriptor 1 for it and point fd 1 at stderr, so
+    # that C-level writers (NCCL's version banner) cannot put anything else on stdout
+    global _JSON_OUT
+    try:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    except OSError:
+        pass
     sys.stdout = sys.stderr
     os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
     ap = argparse.ArgumentParser()

@@ -382,13 +382,17 @@ static constexpr int NUM_EPI2 = 8;                       // two epilogue warps p
 static constexpr int NUM_THREADS2 = 64 + 32 * NUM_EPI2;
 static constexpr int PATCH2_BYTES = 8192;                // per epilogue warp: 2 x 4 KB (double buffer, or hi|lo planes)
 
-template <int BN>
+// DEEP (BN = 256 only): a 4th ring stage paid for with single 4 KB store patches.  The ncu captures of round 2 show the
+// 16-bit-output GEMMs (QKV, FFN-up, conv stack) with the tensor pipe 23-35 % active and neither DRAM nor issue slots busy:
+// with ~1 us of L2 latency the bytes in flight (3 x 48 KB) set the pace, so ring depth is worth more than a double-buffered
+// store patch there.  Residual GEMMs keep the double-buffered patches (their residual tiles are prefetched into them).
+template <int BN, int DEEP = 0>
 struct TcCfg2 {
   static constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   // BN = 64 (narrow outputs: ResNet layer 1/2, conv stack): 4 stages so that two CTAs fit per SM - with so little work
   // per tile, tiles in flight matter more than ring depth.
-  static constexpr int NSTAGE = (BN == 128) ? 4 : 3;
-  static constexpr int PATCH = (BN == 64) ? 4096 : PATCH2_BYTES;   // BN = 64: single 4 KB patch per warp (2 CTAs per SM)
+  static constexpr int NSTAGE = (BN == 128) ? 5 : (DEEP ? 4 : 3);
+  static constexpr int PATCH = (BN == 64 || DEEP) ? 4096 : PATCH2_BYTES;   // single 4 KB patch per warp
   static constexpr int SMEM = NSTAGE * STAGE_BYTES + NUM_EPI2 * PATCH + 1024 + 256;
   static constexpr int MIN_CTAS = (BN == 64) ? 2 : 1;
 };
@@ -467,11 +471,11 @@ DZ_DEVINL void epi_math32(float (&v)[32], const float* __restrict__ bias, float 
   }
 }
 
-template <int BN>
+template <int BN, int DEEP = 0>
 __global__ void __launch_bounds__(NUM_THREADS2, (BN == 64) ? 2 : 1)
 gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiMaps em, const GemmDesc d, const int a_rank5,
                    const int mt, const int nt, const int ntiles, const int mode) {
-  using C = TcCfg2<BN>;
+  using C = TcCfg2<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* patches = smem + C::NSTAGE * C::STAGE_BYTES;
@@ -572,7 +576,7 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
     const bool two = d.out_planes > 1;
     const bool has_res = mode ? (d.res16 != nullptr) : (d.residual != nullptr);
     // double-buffered patches unless both planes are needed (hi | lo share the 8 KB) or the patch is the 4 KB one
-    const bool dbl = (BN != 64) && !(mode && two);
+    const bool dbl = (C::PATCH == PATCH2_BYTES) && !(mode && two);
     const int fp16 = d.fp16;
     const int sw = lane & 7;
     const bool relu_after = d.act_after_res && d.act == 3;
@@ -858,16 +862,16 @@ static cudaError_t launch_bn(const GemmPlan* p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, int DEEP = 0>
 static cudaError_t launch_bn_tma(const GemmPlan* p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_tma_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2<BN, DEEP>::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_tma_kernel<BN><<<p->grid, NUM_THREADS2, TcCfg2<BN>::SMEM, st>>>(p->maps, p->em, p->d, p->rank5, p->mt, p->nt, p->ntiles,
-                                                                            p->epi_mode);
+  gemm_tc_tma_kernel<BN, DEEP><<<p->grid, NUM_THREADS2, TcCfg2<BN, DEEP>::SMEM, st>>>(p->maps, p->em, p->d, p->rank5, p->mt, p->nt,
+                                                                                      p->ntiles, p->epi_mode);
   return cudaGetLastError();
 }
 
@@ -997,7 +1001,13 @@ cudaError_t gemm_plan_launch(const GemmPlan* p, cudaStream_t st) {
     switch (p->bn) {
       case 64: return launch_bn_tma<64>(p, st);
       case 128: return launch_bn_tma<128>(p, st);
-      case 256: return launch_bn_tma<256>(p, st);
+      case 256: {
+        // deep ring when nothing is prefetched into the store patches and one 4 KB patch holds a span (single plane)
+        static const bool no_deep = (getenv("DZ_GEMM_NO_DEEP") != nullptr);
+        const GemmDesc& d = p->d;
+        const bool deep = !no_deep && d.residual == nullptr && d.res16 == nullptr && !(p->epi_mode == 1 && d.out_planes > 1);
+        return deep ? launch_bn_tma<256, 1>(p, st) : launch_bn_tma<256, 0>(p, st);
+      }
     }
     return cudaErrorInvalidValue;
   }
