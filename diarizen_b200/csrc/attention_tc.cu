@@ -36,6 +36,8 @@ struct AttnPlan {
   AttnMaps maps;
   int B;
   size_t smem;
+  int x3 = 0;                 // split-precision kernel (attention_tc3_kernel)
+  CUtensorMap m3[6];          // q hi/lo, k hi/lo, v hi/lo
 };
 
 DZ_DEVINL float ex2(float x) {
@@ -521,6 +523,280 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
   }
 }
 
+// ================================================================================================
+// v3: split-precision (bf16x3, fp32-class) variant of the kernel above for the 1e-3 parity mode - until round 2 that mode fell
+// back to the CUDA-core kernel (50 % of its run time).  Operands arrive as bf16 hi + lo planes; both products are
+// accumulated as three tensor-core passes into the same fp32 accumulator:
+//   S  = Qh Kh^T + Ql Kh^T + Qh Kl^T                      (12 UMMAs of K = 16 per 64-key block)
+//   O += Ph Vh + Pl Vh + Ph Vl                            (the softmax warps write P as hi and lo planes)
+// The ones column that yields the softmax denominator rides on the two Vh passes (N = 80), so the denominator is
+// sum_k (Ph + Pl)[q,k] - exactly the P the numerator uses; the Vl pass runs with N = 64.
+// Shared memory: Q 2 x 16 KB, K / V rings 3 x (8 + 8) KB each, ones block 8 KB, P 2 x (16 + 16) KB = 200 KB: one CTA per SM.
+// Everything else (persistent head-major work list, S ping-pong in TMEM, lazy rescaling, gated bias from the table) is v2.
+// ================================================================================================
+struct AttnMaps3 { CUtensorMap q[2], k[2], v[2]; };
+
+__global__ void __launch_bounds__(A_THREADS, 1) attention_tc3_kernel(const __grid_constant__ AttnMaps3 maps, const AttnArgs a,
+                                                                     const int B) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* Qs = smem;                              // hi 16 KB | lo 16 KB
+  uint8_t* Ks = Qs + 32768;                        // KV_STAGES x (hi 8 KB | lo 8 KB)
+  uint8_t* Vs = Ks + KV_STAGES * 16384;            // KV_STAGES x (hi 8 KB | lo 8 KB), row-major V: MN-major B operand
+  uint8_t* Vc = Vs + KV_STAGES * 16384;            // ones block (second N chunk of the Vh passes)
+  uint8_t* Ps = Vc + 8192;                         // 2 x (hi 16 KB | lo 16 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 32768);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [3]
+  uint64_t* kv_empty = bars + 5;   // [3]
+  uint64_t* s_full = bars + 8;     // [2]
+  uint64_t* p_ready = bars + 10;   // [2]
+  uint64_t* o_ready = bars + 12;
+  uint64_t* o_final = bars + 13;
+  uint64_t* o_free = bars + 14;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  float* tab = reinterpret_cast<float*>(bars + 16);  // [2T-1 + 64 pad]
+
+  const int T = a.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = (T + ABK - 1) / ABK;
+  const int nqt = (T + ABQ - 1) / ABQ;
+  const int n_items = B * a.nheads * nqt;
+  const bool has_bias = a.bias_tab != nullptr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&p_ready[0], 4); mbar_init(&p_ready[1], 4);
+    mbar_init(o_ready, 1);
+    mbar_init(o_final, 1);
+    mbar_init(o_free, 4);
+    mbar_fence_init();
+    for (int i = 0; i < 2; ++i) { tma_prefetch_desc(&maps.q[i]); tma_prefetch_desc(&maps.k[i]); tma_prefetch_desc(&maps.v[i]); }
+  }
+  if (warp == 5) tmem_alloc(tmem_ptr, 256);
+  // ones block: row r (key) has column 0 = 1 (bf16), the rest 0; column 0 sits in 16-byte chunk (0 ^ (r & 7))
+  for (int i = threadIdx.x; i < 2048; i += A_THREADS) {
+    const int r = i >> 5, wd = i & 31;
+    reinterpret_cast<uint32_t*>(Vc)[i] = (wd == ((r & 7) << 2)) ? 0x3F80u : 0u;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t g = 0, n = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        const int qt = it % nqt, pair = it / nqt, b = pair % B, hi = pair / B;
+        if (n > 0) mbar_wait(q_empty, (n - 1) & 1);
+        mbar_expect_tx(q_full, 32768);
+        tma_load_3d(Qs, &maps.q[0], q_full, a.q_col + hi * 64, qt * ABQ, b);
+        tma_load_3d(Qs + 16384, &maps.q[1], q_full, a.q_col + hi * 64, qt * ABQ, b);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const uint32_t s = g % KV_STAGES, use = g / KV_STAGES;
+          if (use > 0) mbar_wait(&kv_empty[s], (use - 1) & 1);
+          mbar_expect_tx(&kv_full[s], 32768);
+          tma_load_3d(Ks + s * 16384, &maps.k[0], &kv_full[s], a.k_col + hi * 64, j * ABK, b);
+          tma_load_3d(Ks + s * 16384 + 8192, &maps.k[1], &kv_full[s], a.k_col + hi * 64, j * ABK, b);
+          tma_load_3d(Vs + s * 16384, &maps.v[0], &kv_full[s], a.v_col + hi * 64, j * ABK, b);
+          tma_load_3d(Vs + s * 16384 + 8192, &maps.v[1], &kv_full[s], a.v_col + hi * 64, j * ABK, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0);
+      const uint32_t idesc_o80 = umma_idesc_bf16(128, 80, 0) | (1u << 16);   // bit 16: B is MN-major
+      const uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0) | (1u << 16);
+      const uint32_t qa = smem_u32(Qs);
+      uint32_t g = 0, n = 0;
+      // S = Qh Kh^T + Ql Kh^T + Qh Kl^T into TMEM buffer (g & 1)
+      auto issue_s = [&](uint32_t gg) {
+        const uint32_t s0 = gg % KV_STAGES;
+        mbar_wait(&kv_full[s0], (gg / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(Ks + s0 * 16384), ts = tmem_base + (gg & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(ts, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(ts, umma_desc_sw128(qa + 16384 + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(ts, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + 8192 + k * 32), idesc_s, 1u);
+        umma_commit(&s_full[gg & 1]);
+      };
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        mbar_wait(q_full, n & 1);
+        issue_s(g);
+        if (nblk == 1) umma_commit(q_empty);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          if (j + 1 < nblk) {
+            issue_s(g + 1);
+            if (j + 2 == nblk) umma_commit(q_empty);   // last read of this item's Q tile
+          }
+          const uint32_t s = g % KV_STAGES;
+          mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
+          if (j == 0 && n > 0) mbar_wait(o_free, (n - 1) & 1);
+          tc_fence_after();
+          const uint32_t pa = smem_u32(Ps + (g & 1) * 32768), va = smem_u32(Vs + s * 16384);
+          const uint32_t lbo = smem_u32(Vc) - va;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // Ph Vh (+ ones column)
+            umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128_mn(va + k * 2048, lbo), idesc_o80, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // Pl Vh (+ ones column)
+            umma_bf16(tmem_O, umma_desc_sw128(pa + 16384 + k * 32), umma_desc_sw128_mn(va + k * 2048, lbo), idesc_o80, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // Ph Vl (64 columns: the denominator must not see it)
+            umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128_mn(va + 8192 + k * 2048, 1024), idesc_o64, 1u);
+          umma_commit(&kv_empty[s]);
+          umma_commit(o_ready);
+        }
+        umma_commit(o_final);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row <-> TMEM lane ----------------
+    const int row = threadIdx.x;  // 0..127
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int sw = row & 7;
+    uint32_t g = 0, n = 0;
+    int cur_h = -1;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+      const int qt = it % nqt, pair = it / nqt, b = pair % B, hi = pair / B;
+      const int tq = qt * ABQ + row;
+      const bool qvalid = tq < T;
+      const float gate = (has_bias && a.gate != nullptr) ? a.gate[((long long)b * a.nheads + hi) * T + (qvalid ? tq : T - 1)] * LOG2E : 0.f;
+      if (has_bias && hi != cur_h) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* src = a.bias_tab + (long long)hi * (2 * T - 1);
+        for (int i = row; i < 2 * T - 1 + 64; i += 128) tab[i] = (i < 2 * T - 1) ? src[i] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_h = hi;
+      }
+      const float* trow = tab + (T - 1) - (qvalid ? tq : T - 1);
+      float m_used = 0.f;
+      for (int j = 0; j < nblk; ++j, ++g) {
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        float r[64];
+        {
+          uint32_t* ru = reinterpret_cast<uint32_t*>(r);
+          const uint32_t ts = tmem_base + (g & 1) * 64 + lane_off;
+          tmem_ld_32x32(ts, ru);
+          tmem_ld_32x32(ts + 32, ru + 32);
+          tmem_ld_wait();
+        }
+        const int kbase = j * ABK;
+        const float negm = -m_used;
+        if (has_bias) {
+          const float* tr = trow + kbase;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) r[c] = fmaf(gate, tr[c], fmaf(r[c], LOG2E, negm));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) r[c] = fmaf(r[c], LOG2E, negm);
+        }
+        if (j == nblk - 1) {
+          const int nvalid = T - kbase;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) r[c] = (c < nvalid) ? r[c] : -INFINITY;
+        }
+        float mx = fmax3(r[0], r[1], r[2]);
+#pragma unroll
+        for (int c = 3; c + 1 < 64; c += 2) mx = fmax3(mx, r[c], r[c + 1]);
+        mx = fmaxf(mx, r[63]);
+        const bool need = (j == 0) || (mx > 8.0f);
+        if (need) {
+          m_used += mx;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) r[c] -= mx;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          const float corr = need ? ex2(-mx) : 1.0f;
+          mbar_wait(o_ready, (g - 1) & 1);
+          tc_fence_after();
+          uint32_t o[32];
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            tmem_ld_32x32(tmem_O + lane_off + hlf * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * corr);
+            tmem_st_32x32(tmem_O + lane_off + hlf * 32, o);
+          }
+          {
+            uint32_t o1[16];
+            tmem_ld_32x32_x16(tmem_O + lane_off + 64, o1);
+            tmem_ld_wait();
+            tmem_st_32x32_x1(tmem_O + lane_off + 64, __float_as_uint(__uint_as_float(o1[0]) * corr));
+          }
+          tmem_st_wait();
+        }
+        uint8_t* prow = Ps + (g & 1) * 32768 + row * 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t wh[4], wl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2(r[8 * c8 + 2 * e]), p1 = ex2(r[8 * c8 + 2 * e + 1]);
+            const uint32_t h2 = pack2_16<0>(p0, p1);                      // bf16 hi pair (p0 in the low half)
+            const float h0 = __uint_as_float(h2 << 16), h1 = __uint_as_float(h2 & 0xffff0000u);
+            wh[e] = h2;
+            wl[e] = pack2_16<0>(p0 - h0, p1 - h1);                        // lo = rn(p - hi)
+          }
+          *reinterpret_cast<uint4*>(prow + ((c8 ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          *reinterpret_cast<uint4*>(prow + 16384 + ((c8 ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g & 1]);
+      }
+      mbar_wait(o_final, n & 1);
+      tc_fence_after();
+      uint32_t o[64], o1[16];
+      tmem_ld_32x32(tmem_O + lane_off, o);
+      tmem_ld_32x32(tmem_O + lane_off + 32, o + 32);
+      tmem_ld_32x32_x16(tmem_O + lane_off + 64, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      if (qvalid) {
+        const float inv = 1.0f / __uint_as_float(o1[0]);
+        bf16* op = a.out + ((long long)b * T + tq) * a.ldo + hi * 64;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            bf16 h0, l0, h1, l1;
+            split_bf16(__uint_as_float(o[8 * c8 + 2 * e]) * inv, h0, l0, 0);
+            split_bf16(__uint_as_float(o[8 * c8 + 2 * e + 1]) * inv, h1, l1, 0);
+            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(op + 8 * c8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (a.out_planes > 1) *reinterpret_cast<uint4*>(op + a.out_plane + 8 * c8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 static bool attn_use_v1() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DZ_ATTN_V1"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -533,6 +809,23 @@ AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B) {
   p->a = a;
   p->B = B;
   const int T = a.T;
+  if (a.planes > 1) {
+    // bf16 hi + lo operand planes: the three-pass kernel (row-major V only, bf16 format)
+    if (a.v == nullptr || a.fp16) { delete p; return nullptr; }
+    uint64_t dims[3] = {(uint64_t)a.ldqk, (uint64_t)T, (uint64_t)B};
+    uint64_t str[3] = {1, (uint64_t)a.ldqk, (uint64_t)T * a.ldqk};
+    uint32_t boxq[3] = {64, ABQ, 1}, boxk[3] = {64, ABK, 1};
+    bool ok = true;
+    for (int pl = 0; pl < 2 && ok; ++pl) {
+      ok = make_tmap_bf16(&p->m3[0 + pl], a.q + pl * a.qk_plane, 3, dims, str, boxq) &&
+           make_tmap_bf16(&p->m3[2 + pl], a.k + pl * a.qk_plane, 3, dims, str, boxk) &&
+           make_tmap_bf16(&p->m3[4 + pl], a.v + pl * a.qk_plane, 3, dims, str, boxk);
+    }
+    if (!ok) { delete p; return nullptr; }
+    p->x3 = 1;
+    p->smem = 1024 + 32768 + 2 * KV_STAGES * 16384 + 8192 + 2 * 32768 + 128 + sizeof(float) * (size_t)(2 * T - 1 + 64 + 8);
+    return p;
+  }
   {
     uint64_t dims[3] = {(uint64_t)a.ldqk, (uint64_t)T, (uint64_t)B};
     uint64_t str[3] = {1, (uint64_t)a.ldqk, (uint64_t)T * a.ldqk};
@@ -561,6 +854,21 @@ AttnPlan* attention_tc_plan_create(const AttnArgs& a, int B) {
 void attention_tc_plan_destroy(AttnPlan* p) { delete p; }
 
 cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
+  if (p->x3) {
+    static size_t attr3 = 0;
+    if (p->smem > attr3) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+      if (e != cudaSuccess) return e;
+      attr3 = p->smem;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const long long items = (long long)((p->a.T + ABQ - 1) / ABQ) * p->a.nheads * p->B;
+    AttnMaps3 m;
+    for (int i = 0; i < 2; ++i) { m.q[i] = p->m3[i]; m.k[i] = p->m3[2 + i]; m.v[i] = p->m3[4 + i]; }
+    attention_tc3_kernel<<<(unsigned)(items < sms ? items : sms), A_THREADS, p->smem, st>>>(m, p->a, p->B);
+    return cudaGetLastError();
+  }
   static size_t attr = 0;
   const bool v1 = attn_use_v1();
   if (p->smem > attr) {

@@ -574,8 +574,9 @@ static int plan_impl(dz_seg* s, int B, int N) {
     at.T = T; at.nheads = h; at.q = qk.p; at.k = qk.p; at.qk_plane = qk.plane; at.ldqk = 3 * h * 64; at.q_col = 0; at.k_col = h * 64;
     at.v = qk.p; at.v_col = 2 * h * 64; at.planes = P; at.bias_tab = tab; at.gate = gatep;
     at.out = ctx.p; at.out_plane = ctx.plane; at.ldo = h * 64; at.out_planes = P; at.fp16 = FP;
-    // the tensor-core attention kernel multiplies the hi planes only; the fp32-class mode uses the CUDA-core kernel
-    const int impl = (s->npass == 3) ? 1 : s->attn_impl;
+    // one-pass modes: attention_tc2_kernel; split-precision mode (hi + lo planes): attention_tc3_kernel (three tensor-core
+    // passes per product); attn_impl = 1 keeps the CUDA-core checker kernel
+    const int impl = s->attn_impl;
     const double aflops = 4.0 * (double)T * T * 64 * h * B;
     if (impl == 0) {
       AttnPlan* ap = attention_tc_plan_create(at, B);
