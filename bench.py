@@ -585,6 +585,54 @@ def run_pipeline_bench(args, world, rank, local, dist):
     emit(out)
 
 
+def run_many_bench(args, world, rank, local, dist):
+    """BASELINE.json configs[4] in miniature: R synthetic recordings (seeds 0..R-1) handed to `DiariZenPipeline.diarize_many` -
+    whole recordings round-robin over the ranks (each rank clusters its own, no collective), the R mod N left over
+    window-sharded with a rotating clustering rank.  Host waveforms in, Annotations out; one step = the whole list."""
+    import tempfile
+    from diarizen_b200.pipeline import DiariZenPipeline
+    seconds, dur, R = args.minutes * 60.0, args.seconds, args.recordings
+    window = int(dur * SR)
+    recs = [synth_meeting(seconds, seed=i).pin_memory() for i in range(R)]
+    probe = DiariZenPipeline.from_random_init(args.arch, seed=0, seg_duration=dur, batch_size=args.batch, classifier_gain=40.0, precision=args.precision)
+    T = probe._segmentation.num_frames(window)
+    emb_sd = centred_embedding_weights(probe, recs[0].cuda(), window, T, seed=0)
+    del probe
+    hub = tempfile.mkdtemp(prefix=f"dz_hub_r{rank}_")
+    build_hub_dir(hub, args.arch, 0, 40.0, dur, args.batch, emb_sd)
+    pipe = DiariZenPipeline.from_pretrained(hub, precision=args.precision)
+    names = [f"rec{i:03d}" for i in range(R)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    pipe.diarize_many(recs[:max(world, 1)], names[:max(world, 1)])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outs = pipe.diarize_many(recs, names)
+    barrier()
+    dt = time.perf_counter() - t0
+    done = torch.tensor([sum(o is not None for o in outs)], device="cuda")
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(done)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    dt = float(tt[0])
+    emit({"metric": METRIC, "value": R * seconds * args.steps / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": 1,
+          "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+          "dtype": {"fp16": "fp16 operands, fp32 accumulate", "bf16": "bf16", "bf16x3": "bf16x3 split (fp32-class)"}[args.precision], "data": "synthetic",
+          "config": {"workload": f"{R} x {args.minutes:g} min synthetic recordings through diarize_many (BASELINE.json configs[4] shape), host waveforms in, Annotations out",
+                     "arch": args.arch, "recordings": R, "annotations_returned": int(done[0]),
+                     "parallelism": f"recordings round-robin over {world} ranks, {R % max(world, 1)} window-sharded with a rotating clustering rank"},
+          "e2e": {"value": R * seconds * args.steps / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(R * seconds * SR * 4), "d2h_bytes_per_step": None},
+          "gpu_launches": None})
+
+
 def seg_sub_record(args):
     """BASELINE.json configs[1] next to the headline: wavlm_base_s80_md, 256 x 5 s windows per step, device resident."""
     from diarizen_b200.segmentation import SegmentationModel
@@ -633,7 +681,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "seg"],
+    ap.add_argument("--recordings", type=int, default=16, help="--workload many: number of recordings in the list")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "seg", "many"],
                     help="pipeline = BASELINE.json configs[2] (large-s80 full pipeline, the metric's configuration); seg = configs[1]")
     ap.add_argument("--arch", default=None)
     ap.add_argument("--seconds", type=float, default=None, help="window length")
@@ -648,14 +697,14 @@ def main():
     ap.add_argument("--no-sub-records", action="store_true")
     ap.add_argument("--even-split", action="store_true", help="window-sharded mode: equal window shares (no smaller share for the clustering rank)")
     args = ap.parse_args()
-    if args.workload == "pipeline":
+    if args.workload in ("pipeline", "many"):
         args.arch = args.arch or "wavlm_large_s80_md"; args.seconds = args.seconds or 16.0; args.batch = args.batch or 32
         args.cpu_windows = args.cpu_windows or 4
     else:
         args.arch = args.arch or "wavlm_base_s80_md"; args.seconds = args.seconds or 5.0; args.batch = args.batch or 256
         args.cpu_windows = args.cpu_windows or 32
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    args.steps = args.steps or ((5 if world_env > 1 else 3) if args.workload == "pipeline" else 10)
+    args.steps = args.steps or ((5 if world_env > 1 else 3) if args.workload == "pipeline" else (1 if args.workload == "many" else 10))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -674,6 +723,12 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    if args.workload == "many":
+        run_many_bench(args, world, rank, local, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.workload == "pipeline":
         run_pipeline_bench(args, world, rank, local, dist)
         if dist is not None:
