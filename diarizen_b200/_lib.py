@@ -142,6 +142,28 @@ def lib() -> C.CDLL:
     L.dz_seg_step_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.dz_seg_profile.restype = C.c_int
     L.dz_seg_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.dz_seg_plan.restype = C.c_int
+    L.dz_seg_plan.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.dz_seg_tap_info.restype = C.c_int
+    L.dz_seg_tap_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dz_seg_run_steps.restype = C.c_int
+    L.dz_seg_run_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dz_fusion_create.restype = C.c_void_p
+    L.dz_fusion_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dz_fusion_destroy.restype = None
+    L.dz_fusion_destroy.argtypes = [C.c_void_p]
+    L.dz_fusion_set_param.restype = C.c_int
+    L.dz_fusion_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.dz_fusion_finalize.restype = C.c_int
+    L.dz_fusion_finalize.argtypes = [C.c_void_p]
+    L.dz_fusion_forward.restype = C.c_int
+    L.dz_fusion_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float,
+                                    C.c_void_p, C.c_void_p]
+    L.dz_rows_to_planes.restype = C.c_int
+    L.dz_rows_to_planes.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.dz_channel_mean.restype = C.c_int
+    L.dz_channel_mean.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.dz_emb_create.restype = C.c_void_p
     L.dz_emb_create.argtypes = [C.c_int, C.c_int]
     L.dz_emb_destroy.restype = None
@@ -196,7 +218,8 @@ EXPORTS = [
     "dz_layernorm", "dz_attention",
     "dz_seg_create", "dz_seg_destroy", "dz_seg_set_param", "dz_seg_finalize", "dz_seg_num_frames",
     "dz_seg_forward", "dz_seg_forward_host", "dz_seg_tap", "dz_seg_last_launches",
-    "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile",
+    "dz_seg_num_steps", "dz_seg_step_info", "dz_seg_profile", "dz_seg_plan", "dz_seg_tap_info", "dz_seg_run_steps",
+    "dz_fusion_create", "dz_fusion_destroy", "dz_fusion_set_param", "dz_fusion_finalize", "dz_fusion_forward", "dz_channel_mean", "dz_rows_to_planes",
     "dz_emb_create", "dz_emb_destroy", "dz_emb_set_param", "dz_emb_finalize", "dz_emb_num_fbank_frames", "dz_emb_forward",
     "dz_emb_last_launches", "dz_emb_tap_fbank", "dz_emb_num_steps", "dz_emb_profile",
     "dz_median_filter", "dz_speaker_count", "dz_embedding_masks", "dz_reconstruct", "dz_pdist", "dz_linkage_workspace_bytes",

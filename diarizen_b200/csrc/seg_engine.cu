@@ -548,6 +548,7 @@ static int plan_impl(dz_seg* s, int B, int N) {
     p.layernorm("tr_ln", ln);
   }
   p.tap_f32("rep0", xres, R, D, Dp);
+  p.tap_bf("xbf", xbf, R, D, Dp);   // 16-bit operand copy of the residual stream (post-norm models read it as the next layer's input)
 
   // relative-position bias table for this T: tab[hi][d + T - 1] = E[bucket(d)][head]   (layer 0 owns E)
   bool have_bias = a.num_heads[0] > 0;
@@ -799,6 +800,54 @@ int dz_seg_num_frames(const dz_seg* s, int num_samples) {
     n = (n - CONV_K[l]) / CONV_S[l] + 1;
   }
   return n;
+}
+
+/* ---- step-range execution: the hooks the multi-channel model (diarizen_b200/segmentation_mc.py) uses to interleave its channel
+ * fusion modules with the layers of this engine (components.py:1026-1070) ---- */
+int dz_seg_plan(dz_seg* s, int B, int N) {
+  if (!s || !s->finalized) return fail(DZ_ERR_STATE, "dz_seg_finalize has not been called");
+  if (s->B == B && s->N == N) return DZ_OK;
+  cudaDeviceSynchronize();
+  int r = plan_impl(s, B, N);
+  if (r != DZ_OK) return r;
+  cudaError_t e = cudaDeviceSynchronize();
+  return e == cudaSuccess ? DZ_OK : fail(DZ_ERR_CUDA, std::string("plan failed: ") + cudaGetErrorString(e));
+}
+/* named intermediate of the current plan: device pointer (fp32 rows, or 16-bit planes when *is16 = 1), geometry, and the number of
+ * steps after which it holds its value */
+int dz_seg_tap_info(dz_seg* s, const char* name, void** ptr, int64_t* plane_elems, int64_t* rows, int* cols, int* ld, int* step, int* is16) {
+  if (!s || !name) return fail(DZ_ERR_INVALID, "bad argument");
+  auto it = s->taps.find(name);
+  if (it == s->taps.end()) return fail(DZ_ERR_INVALID, std::string("unknown tap '") + name + "'");
+  const Tap& t = it->second;
+  if (ptr) *ptr = t.f32 ? (void*)t.f32 : (void*)t.bf;
+  if (plane_elems) *plane_elems = t.bf_plane;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.C;
+  if (ld) *ld = t.ld;
+  if (step) *step = t.step;
+  if (is16) *is16 = t.f32 ? 0 : 1;
+  return DZ_OK;
+}
+/* runs steps [first, last) of the plan for (B, N); wav / logp / multilabel as in dz_seg_forward (only read by the steps that use them) */
+int dz_seg_run_steps(dz_seg* s, const float* wav_dev, int B, int N, int first, int last, float* logp_dev, uint8_t* multilabel_dev, void* stream) {
+  if (!s) return fail(DZ_ERR_INVALID, "null handle");
+  int r = dz_seg_plan(s, B, N);
+  if (r != DZ_OK) return r;
+  if (last < 0 || last > (int)s->steps.size()) last = (int)s->steps.size();
+  if (first < 0 || first > last) return fail(DZ_ERR_INVALID, "bad step range");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!s->done_event) cudaEventCreateWithFlags(&s->done_event, cudaEventDisableTiming);
+  if (s->ran && s->last_stream != st) cudaStreamWaitEvent(st, s->done_event, 0);
+  s->cur_wav = wav_dev; s->cur_logp = logp_dev; s->cur_ml = multilabel_dev;
+  for (int i = first; i < last; ++i) {
+    cudaError_t e = s->steps[i].fn(st);
+    if (e != cudaSuccess) return fail(DZ_ERR_CUDA, "launch '" + s->steps[i].name + "' failed: " + cudaGetErrorString(e));
+  }
+  s->last_launches = last - first;
+  cudaEventRecord(s->done_event, st);
+  s->last_stream = st; s->ran = true;
+  return DZ_OK;
 }
 
 int dz_seg_forward(dz_seg* s, const float* wav_dev, int B, int N, float* logp_dev, uint8_t* multilabel_dev, void* stream) {

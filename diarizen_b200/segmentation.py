@@ -152,6 +152,30 @@ class SegmentationModel:
                                                    C.c_void_p(logp.data_ptr()), C.c_void_p(ml.data_ptr())))
         return logp, ml
 
+    # --- step-range execution (used by the multi-channel model to interleave its fusion modules with the layers) ---
+    def plan(self, B: int, N: int) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.dz_seg_plan(self._h, B, N))
+
+    def tap_info(self, name: str) -> dict:
+        ptr, plane, rows = C.c_void_p(), C.c_int64(), C.c_int64()
+        cols, ld, step, is16 = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self._L.dz_seg_tap_info(self._h, name.encode(), C.byref(ptr), C.byref(plane), C.byref(rows), C.byref(cols), C.byref(ld),
+                                           C.byref(step), C.byref(is16)))
+        return {"ptr": ptr.value, "plane": plane.value, "rows": rows.value, "cols": cols.value, "ld": ld.value, "step": step.value, "is16": bool(is16.value)}
+
+    def run_steps(self, B: int, N: int, first: int, last: int, wav: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None,
+                  ml: Optional[torch.Tensor] = None) -> None:
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._L.dz_seg_run_steps(self._h, C.c_void_p(wav.data_ptr()) if wav is not None else None, B, N, first, last,
+                                                C.c_void_p(logp.data_ptr()) if logp is not None else None,
+                                                C.c_void_p(ml.data_ptr()) if ml is not None else None, C.c_void_p(st)))
+
+    @property
+    def num_steps(self) -> int:
+        return self._L.dz_seg_num_steps(self._h)
+
     def tap(self, name: str) -> torch.Tensor:
         """Debug: fp32 copy of a named intermediate of the last forward (rows, C)."""
         with torch.cuda.device(self.device):

@@ -146,6 +146,27 @@ int dz_seg_forward(dz_seg* s, const float* wav_dev, int B, int N, float* logp_de
 int dz_seg_forward_host(dz_seg* s, const float* wav_host, int B, int N, float* logp_host, uint8_t* multilabel_host);
 /* Debug tap: copy a named intermediate of the last forward (fp32) into dst_dev; returns element count or <0. */
 int64_t dz_seg_tap(dz_seg* s, const char* name, float* dst_dev, int64_t capacity);
+/* Step-range execution for callers that interleave their own device work with the engine's layers (the multi-channel model,
+ * diarizen/models/module/wav2vec2/components.py:1026-1070): plan a batch shape, look up a named intermediate of the plan
+ * ("rep<l>" = the residual stream after layer l, "mix" = the layer-mix accumulator, "xbf" = its 16-bit operand copy) and run a
+ * range of steps. */
+int dz_seg_plan(dz_seg* s, int B, int N);
+int dz_seg_tap_info(dz_seg* s, const char* name, void** ptr, int64_t* plane_elems, int64_t* rows, int* cols, int* ld, int* step, int* is16);
+int dz_seg_run_steps(dz_seg* s, const float* wav_dev, int B, int N, int first, int last, float* logp_dev, uint8_t* multilabel_dev, void* stream);
+
+/* Cross-channel fusion module of the multi-channel model (diarizen/models/module/utils_mc.py:13-64): x (B, C, T, D) fp32, rows
+ * ordered (b, c, t), updated in place: x <- LayerNorm(Linear_O(attention over channels(Linear_QKV(x)))) + x.
+ * Parameters by the reference's state-dict names: linearQ/K/V/O.{weight,bias}, ln_norm.{weight,bias}. */
+typedef struct dz_fusion dz_fusion;
+dz_fusion* dz_fusion_create(int D, int hidden, int heads, int precision);
+void dz_fusion_destroy(dz_fusion* f);
+int dz_fusion_set_param(dz_fusion* f, const char* name, const float* host, int64_t n);
+int dz_fusion_finalize(dz_fusion* f);
+int dz_fusion_forward(dz_fusion* f, float* x_dev, int B, int C, int T, int ldx, void* xbf_dev, int64_t xbf_plane, int ldb, float* mix_dev,
+                      float mix_w, float* att_dev, void* stream);
+int dz_rows_to_planes(const float* x_dev, int64_t rows, int C, int ldx, void* out_dev, int64_t plane_elems, int ldo, int planes, int fp16, void* stream);
+/* out[(b, t)] = mean over channels of in[(b, c, t)], fp32 rows of width D with leading dimension ld */
+int dz_channel_mean(const float* in_dev, float* out_dev, int B, int C, int T, int D, int ld, void* stream);
 /* Kernel launches issued by the last dz_seg_forward call. */
 int dz_seg_last_launches(const dz_seg* s);
 /* Launch list of the current plan: name and algorithmic FLOPs (2*M*N*K for GEMMs, 4*T*T*64*h*B for attention,

@@ -9,7 +9,8 @@ from oracle.seg_oracle import seg_forward
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
 
 
-@pytest.mark.parametrize("name,N", [("tiny_base", 16000), ("tiny_large", 16000), ("wavlm_base_s80_md", 24000)])
+@pytest.mark.parametrize("name,N", [("tiny_base", 16000), ("tiny_large", 16000), ("wavlm_base_s80_md", 24000),
+                                    ("wavlm_large_s80_md", 48000)])      # the benchmarked architecture
 def test_seg_oracle_equals_reference(name, N):
     a = get_arch(name)
     m = ref_loader.RefSegModel(a).eval()
