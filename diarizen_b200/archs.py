@@ -87,6 +87,9 @@ ARCHS: Dict[str, SegArch] = {
     # tiny shapes for fixtures / CPU tests (not a reference variant)
     "tiny_base": SegArch("tiny_base", False, (24, 20, 28, 20, 36, 20, 28), 128, 2, ((0, 1), (), (1,)), (72, 40, 0),
                          head_dim_model=64, head_ffn=96, head_heads=1, head_layers=1),
+    # five small post-norm layers: room for the four channel-fusion modules of the multi-channel recipe
+    "tiny_base_mc": SegArch("tiny_base_mc", False, (24, 20, 28, 20, 36, 20, 28), 128, 2, ((0, 1), (1,), (0,), (0, 1), (1,)),
+                            (72, 40, 56, 40, 48), head_dim_model=64, head_ffn=96, head_heads=1, head_layers=1),
     "tiny_large": SegArch("tiny_large", True, (32, 20, 28, 20, 36, 20, 28), 128, 2, ((1,), (), (0, 1)), (72, 0, 40),
                           head_dim_model=64, head_ffn=96, head_heads=1, head_layers=2),
 }

@@ -122,7 +122,7 @@ class DiariZenPipeline:
     def __init__(self, diarizen_hub, embedding_model, config_parse: Optional[Dict[str, Any]] = None,
                  rttm_out_dir: Optional[str] = None, *, precision: str = "fp16", device=None,
                  _seg: Optional[SegmentationModel] = None, _emb: Optional[EmbeddingModel] = None, _config: Optional[dict] = None,
-                 segmentation: Optional[list] = None):
+                 segmentation: Optional[list] = None, _mc=None):
         if _config is None:
             diarizen_hub = Path(diarizen_hub)
             config = _load_toml(diarizen_hub / "config.toml")
@@ -186,7 +186,17 @@ class DiariZenPipeline:
                                                                     ("num_layer", "head_layers"), ("kernel_size", "head_kernel")) if theirs in margs}
             if head:
                 arch = dataclasses.replace(arch, **head)
-            _seg = SegmentationModel(arch, sd, precision=precision, device=self.device)
+            if "channel_fusion_layers" in margs or str(config["model"].get("path", "")).endswith("model_wavlm_conformer_mc.Model"):
+                # multi-channel model (model_wavlm_conformer_mc.py:26-57): its single-channel continuation engine doubles as
+                # `_segmentation` (frame geometry, specifications); every input goes through `diarize_session`
+                from .segmentation_mc import MCSegmentationModel
+                self._segmentation_mc = MCSegmentationModel(arch, sd, fusion_dim=int(margs.get("channel_fusion_dim", 768)),
+                                                            fusion_heads=int(margs.get("channel_fusion_heads", 4)),
+                                                            fusion_layers=int(margs.get("channel_fusion_layers", 4)),
+                                                            precision=precision, device=self.device)
+                _seg = self._segmentation_mc._merged
+            else:
+                _seg = SegmentationModel(arch, sd, precision=precision, device=self.device)
         if _emb is None:
             esd = torch.load(str(embedding_model), map_location="cpu")
             esd = esd.get("state_dict", esd)
@@ -201,6 +211,8 @@ class DiariZenPipeline:
         self._L = _lib.lib()
         self.last = {}
         self._tails = {}
+        if not hasattr(self, "_segmentation_mc"):
+            self._segmentation_mc = _mc
         # window-sharded mode: fraction of an even window share that the clustering rank takes (None = even split); see
         # sharding.window_ranges.  DZ_ROOT_SHARE overrides.
         self.root_share = float(os.environ["DZ_ROOT_SHARE"]) if os.environ.get("DZ_ROOT_SHARE") else None
@@ -247,12 +259,20 @@ class DiariZenPipeline:
                          ahc_threshold: float = 0.70, min_speakers: int = 1, max_speakers: int = 20,
                          apply_median_filtering: bool = True, classifier_gain: float = 1.0, precision: str = "fp16",
                          rttm_out_dir: Optional[str] = None, device=None, emb_state_dict=None,
-                         vbx: Optional[dict] = None) -> "DiariZenPipeline":
+                         vbx: Optional[dict] = None, multichannel: Optional[dict] = None, seg_state_dict=None) -> "DiariZenPipeline":
         """Seeded random weights of the named architecture (no checkpoint is reachable offline: SURVEY.md 0.8)."""
         from .archs import init_resnet_state_dict
         dev = torch.device(device if device is not None else "cuda")
         arch = get_arch(arch_name)
-        seg = SegmentationModel(arch, init_state_dict(arch, seed, classifier_gain), precision=precision, device=dev)
+        sd = seg_state_dict if seg_state_dict is not None else init_state_dict(arch, seed, classifier_gain)
+        mc = None
+        if multichannel is not None:
+            # multichannel = {"fusion_dim": ..., "fusion_heads": ..., "fusion_layers": ...}; `seg_state_dict` must hold channel_fusions.*
+            from .segmentation_mc import MCSegmentationModel
+            mc = MCSegmentationModel(arch, sd, precision=precision, device=dev, **multichannel)
+            seg = mc._merged
+        else:
+            seg = SegmentationModel(arch, sd, precision=precision, device=dev)
         emb = EmbeddingModel(emb_state_dict if emb_state_dict is not None else init_resnet_state_dict(seed), precision=precision, device=dev)
         config = {
             "model": {"args": {"wavlm_src": arch_name}},
@@ -266,7 +286,7 @@ class DiariZenPipeline:
             config["clustering"]["args"].update({"method": "VBxClustering", "Fa": 0.07, "Fb": 0.8, "lda_dim": 128,
                                                  "max_iters": 20})
             config["clustering"]["args"].update(vbx)
-        return cls(None, None, rttm_out_dir=rttm_out_dir, precision=precision, device=dev, _seg=seg, _emb=emb, _config=config)
+        return cls(None, None, rttm_out_dir=rttm_out_dir, precision=precision, device=dev, _seg=seg, _emb=emb, _config=config, _mc=mc)
 
     # ------------------------------------------------------------------------------------------------
     def _windows(self, num_samples: int):
@@ -475,6 +495,63 @@ class DiariZenPipeline:
         self.collect_timing = keep
         self.root_share = float(share.item())
         return self.root_share
+
+    # ------------------------------------------------------------------------------------------------
+    # multi-channel recordings: recipes/diar_ssl_mc/infer_avg.py:47-118 `diarize_session`
+    # ------------------------------------------------------------------------------------------------
+    def diarize_multichannel(self, wav: torch.Tensor) -> Dict[str, Any]:
+        """wav (channels, samples) fp32 -> the same dict as `diarize_waveform`.  Windows of all channels go through the
+        multi-channel segmentation model; speaker embeddings are extracted per channel with the shared masks and averaged with
+        the channel weights the model's 4th fusion module attends with (mean over frames and query channels of its attention
+        map: infer_avg.py:33-45 `att_enhanced_emb`); everything after that is the single-channel path."""
+        if self._segmentation_mc is None:
+            raise RuntimeError("this pipeline was built with a single-channel segmentation model")
+        dev, S = self.device, 4
+        self._timing, self._t_last = {}, None
+        with torch.cuda.device(dev):
+            self._mark(None)
+            Cch, Nw = wav.shape
+            window, step, Cn = self._windows(Nw)
+            T = self._segmentation.num_frames(window)
+            pad_to = (Cn - 1) * step + window
+            wdev = torch.zeros((Cch, max(pad_to, Nw)), device=dev, dtype=torch.float32)
+            wdev[:, :Nw] = wav.to(dev, torch.float32)
+            chunks = wdev.as_strided((Cn, Cch, window), (step, wdev.stride(0), 1))
+            raw = torch.zeros((Cn, T, S), device=dev, dtype=torch.uint8)
+            F = self._segmentation_mc.fusion_layers
+            sel = 3 if F > 3 else F - 1                       # the recipe reads fusion module 3 (of 4)
+            weights = torch.empty((Cn, Cch), device=dev, dtype=torch.float32)
+            bs = max(1, self.segmentation_batch_size)
+            for a in range(0, Cn, bs):
+                b = min(a + bs, Cn)
+                _, ml, att = self._segmentation_mc.hard(chunks[a:b].contiguous(), want_logp=False)
+                raw[a:b] = ml
+                weights[a:b] = att[:, sel].mean(dim=(1, 2))    # (windows, T, C, C) -> weight of channel j = mean over t, i
+            self._mark("segmentation")
+            # masks as in the single-channel path, then one embedding pass per channel on that channel's audio
+            emb = torch.zeros((Cn, S, 256), device=dev, dtype=torch.float32)
+            seg = stats = None
+            for ch in range(Cch):
+                seg, stats, e = self._masks_and_embeddings(raw, wdev[ch], wdev[ch].as_strided((Cn, window), (step, 1)), window, step, T, 0, Cn, Cn)
+                emb += weights[:, ch, None, None] * e
+            self.last_raw = raw
+            self.last_channel_weights = weights
+            return self._back(seg, stats, emb, Cn, T)
+
+    def diarize_session(self, in_wav, sess_name=None):
+        """multi-channel counterpart of `__call__`: every channel of the file is used (the single-channel `__call__` keeps
+        channel 0 only, inference.py:128)."""
+        if isinstance(in_wav, dict):
+            w = torch.as_tensor(in_wav["waveform"], dtype=torch.float32)
+            w = w[None] if w.dim() == 1 else w
+            sr = int(in_wav.get("sample_rate", SR))
+        else:
+            x, sr = _read_wav(in_wav)
+            w = torch.from_numpy(np.ascontiguousarray(x.T))
+        if sr != SR:
+            w = torch.stack([_to_16k(c, sr) for c in w])
+        print("Extracting segmentations...")
+        return self._finish(self.diarize_multichannel(w), sess_name)
 
     def diarize_segmentations(self, raw_segmentations, embeddings) -> Dict[str, Any]:
         """Stage 2 alone: (C,T,4) {0,1} window decisions as they leave the segmentation network and (C,4,256) embeddings ->

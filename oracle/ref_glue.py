@@ -202,7 +202,9 @@ def load():
     if "diarizen.pipelines" not in sys.modules:
         import diarizen.pipelines  # noqa: F401  (real package: __init__ is empty)
     dz = _load("diarizen.pipelines.inference", os.path.join(REF, "diarizen", "pipelines", "inference.py"))
-    _NS = types.SimpleNamespace(core=core, io=io, inference=inf, signal=sig, diarization=dia, clustering=clu, speaker_diarization=sd,
+    _mod("pyannote.metrics.segmentation", Annotation=core.Annotation, Segment=core.Segment)
+    mc = _load("ref_recipe_diar_ssl_mc_infer_avg", os.path.join(REF, "recipes", "diar_ssl_mc", "infer_avg.py"))
+    _NS = types.SimpleNamespace(mc_recipe=mc, core=core, io=io, inference=inf, signal=sig, diarization=dia, clustering=clu, speaker_diarization=sd,
                                 dz=dz, powerset=ps, receptive_field=rf, Model=Model, Specifications=Specifications,
                                 Problem=Problem, Resolution=Resolution)
     return _NS
@@ -343,4 +345,101 @@ def run_reference_pipeline(pipe, wav: np.ndarray, sess_name: str = "sess"):
         pipe.clustering.__class__.__call__ = orig_clu
     cap["rttm"] = ann.to_rttm()
     cap["turns"] = [(s.start, s.end, l) for s, _, l in ann.itertracks(yield_label=True)]
+    return cap
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the multi-channel recipe: recipes/diar_ssl_mc/infer_avg.py `diarize_session` around the reference MC model parts
+# ------------------------------------------------------------------------------------------------------------
+def build_reference_mc_pipeline(arch, seg_state_dict, emb_state_dict, fusion: dict, seg_duration: float, segmentation_step: float = 0.1,
+                                batch_size: int = 8, ahc_threshold: float = 0.70, min_cluster_size: int = 3):
+    """-> a pyannote `SpeakerDiarization` object as recipes/diar_ssl_mc/infer_avg.py builds it (minus checkpoint loading): its
+    segmentation model is oracle/ref_loader.RefSegModelMC (the reference's own wav2vec2 / fusion / conformer modules), the
+    embedding model the pinned ResNet oracle."""
+    ns = load()
+    from oracle import ref_loader
+    from oracle.emb_oracle import emb_forward
+    core = ns.core
+    inner = ref_loader.RefSegModelMC(arch, **fusion).eval()
+    inner.load_state_dict(seg_state_dict, strict=False)
+
+    class SegModel(ns.Model):
+        def __init__(self):
+            super().__init__()
+            self.inner = inner
+            self.sample_rate = 16000
+            self.audio = ns.io.Audio(sample_rate=16000, mono=None)          # core/model.py:152-157: num_channels > 1 => no downmix
+            self.specifications = ns.Specifications(problem=ns.Problem.MONO_LABEL_CLASSIFICATION, resolution=ns.Resolution.FRAME,
+                                                    duration=seg_duration, warm_up=(0.0, 0.0), classes=[f"speaker#{i + 1}" for i in range(4)],
+                                                    powerset_max_classes=2, permutation_invariant=True)
+            self._receptive_field = core.SlidingWindow(start=(79 - 199.5) / 16000, duration=400 / 16000, step=320 / 16000)
+
+        @property
+        def device(self):
+            return next(self.inner.parameters()).device
+
+        def forward(self, waveforms):
+            return self.inner(waveforms)
+
+    class Embedding:
+        sample_rate, dimension, metric, min_num_samples = 16000, 256, "cosine", 400
+
+        def __call__(self, waveforms, masks=None):
+            return emb_forward(emb_state_dict, waveforms[:, 0, :], masks[:, None, :])[:, 0].numpy()
+
+    P = ns.speaker_diarization.SpeakerDiarization
+    pipe = object.__new__(P)
+    model = SegModel()
+    pipe.model = model
+    pipe.segmentation_step = segmentation_step
+    pipe.embedding_batch_size = batch_size
+    pipe.embedding_exclude_overlap = True
+    pipe._segmentation = ns.inference.Inference(model, duration=seg_duration, step=segmentation_step * seg_duration, skip_aggregation=True,
+                                                batch_size=batch_size, device=torch.device("cpu"))
+    pipe._embedding = Embedding()
+    pipe._audio = ns.io.Audio(sample_rate=16000, mono="downmix")
+    pipe.clustering = ns.clustering.Clustering["AgglomerativeClustering"].value(metric="cosine")
+    pipe.clustering.instantiate({"method": "centroid", "min_cluster_size": min_cluster_size, "threshold": ahc_threshold})
+    return pipe
+
+
+def run_reference_mc_session(pipe, wav_mc: np.ndarray, sess_name: str = "sess", min_speakers=1, max_speakers=20):
+    """recipes/diar_ssl_mc/infer_avg.py:47-118 `diarize_session` on an in-memory (channels, samples) waveform."""
+    ns = load()
+    import torchaudio
+    cap = {}
+    P = type(pipe)
+    orig_seg, orig_rec = P.get_segmentations, P.reconstruct
+    orig_clu = pipe.clustering.__class__.__call__
+
+    def get_segmentations(self, file, hook=None, soft=False):
+        out = orig_seg(self, file, hook=hook, soft=soft)
+        cap["raw_segmentations"] = out[0].data.copy()
+        cap["attention"] = np.array(out[1], copy=True)
+        return out
+
+    def reconstruct(self, seg, hard, count):
+        cap["segmentations"] = seg.data.copy()
+        cap["hard_clusters"] = np.array(hard, copy=True)
+        cap["count"] = count.data.copy()
+        out = orig_rec(self, seg, hard, count)
+        cap["discrete"] = out[0].data.copy()
+        return out
+
+    def clu_call(self, *a, **k):
+        cap["embeddings"] = np.array(k["embeddings"], copy=True)
+        return orig_clu(self, *a, **k)
+
+    real_load = torchaudio.load
+    w = torch.as_tensor(wav_mc, dtype=torch.float32)
+    torchaudio.load = lambda path: (w, 16000)
+    P.get_segmentations, P.reconstruct = get_segmentations, reconstruct
+    pipe.clustering.__class__.__call__ = clu_call
+    try:
+        ann = ns.mc_recipe.diarize_session(sess_name, "in-memory.wav", pipe, min_speakers=min_speakers, max_speakers=max_speakers)
+    finally:
+        torchaudio.load = real_load
+        P.get_segmentations, P.reconstruct = orig_seg, orig_rec
+        pipe.clustering.__class__.__call__ = orig_clu
+    cap["rttm"] = ann.to_rttm()
     return cap

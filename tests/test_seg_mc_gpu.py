@@ -34,3 +34,33 @@ def test_multichannel_forward(arch, precision, tol):
     assert torch.equal(logp, logp2)
     _, _, att1 = m.hard(torch.from_numpy(z["wav"][:, :1]))
     assert torch.allclose(att1, torch.ones_like(att1))
+
+
+def test_multichannel_session_matches_reference_recipe():
+    """`DiariZenPipeline.diarize_session` on a 3-channel recording == the reference recipe's `diarize_session`
+    (recipes/diar_ssl_mc/infer_avg.py:47-118, run through oracle/ref_glue.py around the reference's own MC model modules):
+    window decisions, channel weights, attention-weighted embeddings, clusters and RTTM text."""
+    from diarizen_b200.archs import get_arch, init_state_dict
+    from diarizen_b200.pipeline import DiariZenPipeline
+    z = np.load(os.path.join(G, "glue_mc_session.npz"))
+    a = get_arch("tiny_base_mc")
+    sd = init_state_dict(a, int(z["weights_seed"]), float(z["classifier_gain"]))
+    sd.update({k[len("fusion."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("fusion.")})
+    pipe = DiariZenPipeline.from_random_init("tiny_base_mc", seed=int(z["weights_seed"]), seg_duration=float(z["seg_duration"]), batch_size=8,
+                                             min_cluster_size=int(z["min_cluster_size"]), classifier_gain=float(z["classifier_gain"]),
+                                             precision="bf16x3", seg_state_dict=sd,
+                                             multichannel=dict(fusion_dim=int(z["cfg_fusion_dim"]), fusion_heads=int(z["cfg_fusion_heads"]),
+                                                               fusion_layers=int(z["cfg_fusion_layers"])))
+    wav = torch.from_numpy(z["wav_i16"].astype(np.float32) / 32768.0)
+    ann = pipe.diarize_session({"waveform": wav, "sample_rate": 16000}, sess_name="sess")
+    res = pipe.last
+    flips = np.argwhere(pipe.last_raw.cpu().numpy() != z["raw_segmentations"])
+    assert flips.size == 0, f"{len(flips)} window decisions differ, first {flips[:5].tolist()}"
+    w_ref = z["attention3"].mean(axis=(1, 2))
+    assert np.abs(pipe.last_channel_weights.cpu().numpy() - w_ref).max() < 1e-3
+    assert np.array_equal(res["segmentations"].cpu().numpy(), z["segmentations"])
+    scale = np.abs(z["embeddings"]).max()
+    assert np.abs(res["embeddings"] - z["embeddings"]).max() / scale < 2e-3
+    assert np.array_equal(res["hard_clusters"], z["hard_clusters"])
+    assert np.array_equal(res["discrete"], z["discrete"])
+    assert ann.to_rttm() == str(z["rttm"])
