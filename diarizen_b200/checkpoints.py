@@ -76,12 +76,13 @@ def select_checkpoints(val_metric_lst: List[Dict], val_metric: str = "Loss", val
 
 
 def write_hub_snapshot(root: Union[str, Path], arch, seg_state_dict: Dict[str, torch.Tensor], emb_state_dict: Dict[str, torch.Tensor],
-                       inference_args: Dict, clustering_args: Dict, plda: tuple = None) -> Path:
+                       inference_args: Dict, clustering_args: Dict, plda: tuple = None, fusion: Dict = None) -> Path:
     """Saves a model pair in the directory layout `DiariZenPipeline(diarizen_hub=...)` / `from_pretrained(<dir>)` read
     (diarizen/pipelines/inference.py:34-50,95-119): `config.toml`, `pytorch_model.bin` (full segmentation state dict),
     `<arch>.pt` = the WavLM `{config, state_dict}` checkpoint `model.args.wavlm_src` points at
     (model_wavlm_conformer.py:209-221), `wespeaker/pytorch_model.bin` in the lightning `{"state_dict": ...}` wrapping
-    (core/model.py:460-473) and, when `plda = (xvec_transform dict, plda dict)` is given, `plda/*.npz` for VBx."""
+    (core/model.py:460-473) and, when `plda = (xvec_transform dict, plda dict)` is given, `plda/*.npz` for VBx.  `fusion`
+    ({"fusion_dim", "fusion_heads", "fusion_layers"}) marks a multi-channel model (its state dict holds `channel_fusions.*`)."""
     import numpy as np
     from .archs import to_reference_config
     root = Path(root)
@@ -106,6 +107,9 @@ def write_hub_snapshot(root: Union[str, Path], arch, seg_state_dict: Dict[str, t
         return "".join(f"{k} = {val(v)}\n" for k, v in d.items())
     head = {"attention_in": arch.head_dim_model, "ffn_hidden": arch.head_ffn, "num_head": arch.head_heads, "num_layer": arch.head_layers,
             "kernel_size": arch.head_kernel, "wavlm_layer_num": arch.num_layers + 1, "wavlm_feat_dim": arch.embed_dim}
+    if fusion is not None:   # multi-channel model (model_wavlm_conformer_mc.py:26-57): channel_fusion_dim / _layers / _heads
+        head.update({"channel_fusion_dim": fusion["fusion_dim"], "channel_fusion_layers": fusion["fusion_layers"],
+                     "channel_fusion_heads": fusion["fusion_heads"]})
     with open(root / "config.toml", "w") as f:
         f.write(f"[model.args]\nwavlm_src = \"{src}\"\n{table(head)}\n[inference.args]\n{table(inference_args)}\n[clustering.args]\n{table(clustering_args)}")
     return root

@@ -64,3 +64,22 @@ def test_multichannel_session_matches_reference_recipe():
     assert np.array_equal(res["hard_clusters"], z["hard_clusters"])
     assert np.array_equal(res["discrete"], z["discrete"])
     assert ann.to_rttm() == str(z["rttm"])
+
+
+def test_multichannel_hub_directory(tmp_path):
+    """config.toml with channel_fusion_* model args -> the multi-channel model is built by the hub-directory loader"""
+    from diarizen_b200.archs import get_arch, init_resnet_state_dict, init_state_dict
+    from diarizen_b200.checkpoints import write_hub_snapshot
+    from diarizen_b200.pipeline import DiariZenPipeline
+    z = np.load(os.path.join(G, "glue_mc_session.npz"))
+    a = get_arch("tiny_base_mc")
+    sd = init_state_dict(a, int(z["weights_seed"]), float(z["classifier_gain"]))
+    sd.update({k[len("fusion."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("fusion.")})
+    fusion = dict(fusion_dim=int(z["cfg_fusion_dim"]), fusion_heads=int(z["cfg_fusion_heads"]), fusion_layers=int(z["cfg_fusion_layers"]))
+    write_hub_snapshot(tmp_path / "hub", a, sd, init_resnet_state_dict(int(z["weights_seed"])),
+                       {"seg_duration": 5.0, "segmentation_step": 0.1, "batch_size": 8, "apply_median_filtering": True},
+                       {"method": "AgglomerativeClustering", "min_speakers": 1, "max_speakers": 20, "ahc_criterion": "distance", "ahc_threshold": 0.70,
+                        "min_cluster_size": int(z["min_cluster_size"])}, fusion=fusion)
+    pipe = DiariZenPipeline.from_pretrained(str(tmp_path / "hub"), precision="bf16x3")
+    wav = torch.from_numpy(z["wav_i16"].astype(np.float32) / 32768.0)
+    assert pipe.diarize_session({"waveform": wav, "sample_rate": 16000}, sess_name="sess").to_rttm() == str(z["rttm"])
