@@ -116,9 +116,11 @@ def main(argv=None, pipeline_factory=None) -> int:
             config["clustering"]["args"]["plda_dir"] = os.path.join(args.diarizen_hub, "plda")
         pipe = pipeline_factory(None, args.embedding_model, rttm_out_dir=args.out_dir, precision=args.precision, _config=config,
                                 segmentation=checkpoints_from_args(args))
+        # a multi-channel model (recipes/diar_ssl_mc: `channel_fusion_*` in the model section) uses every channel of the file
+        run = pipe.diarize_session if getattr(pipe, "_segmentation_mc", None) is not None else pipe
         for sess, in_wav in load_scp(args.in_wav_scp).items():
             print(f"Diarizing Session: {sess}")
-            pipe(in_wav, sess_name=sess)
+            run(in_wav, sess_name=sess)
         return 0
     if not args.diarizen_hub:
         raise SystemExit("hub mode needs --diarizen_hub")
