@@ -618,8 +618,15 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
           tmem_ld_32x32(tmem_acc + (uint32_t)(g * 32), r);
           tmem_ld_wait();
           const int nrem = d.N - g * 32;
+          if (nrem >= 32) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum += (j < nrem) ? __uint_as_float(r[j]) : 0.f;
+            for (int j = 0; j < 32; j += 4) { s0 += __uint_as_float(r[j]); s1 += __uint_as_float(r[j + 1]); s2 += __uint_as_float(r[j + 2]); s3 += __uint_as_float(r[j + 3]); }
+            sum += (s0 + s1) + (s2 + s3);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += (j < nrem) ? __uint_as_float(r[j]) : 0.f;
+          }
         }
         ln_mean = sum / (float)d.N;
         float ssq = 0.f;
@@ -629,8 +636,19 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
           tmem_ld_32x32(tmem_acc + (uint32_t)(g * 32), r);
           tmem_ld_wait();
           const int nrem = d.N - g * 32;
+          if (nrem >= 32) {
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float c = __uint_as_float(r[j]) - ln_mean; ssq += (j < nrem) ? c * c : 0.f; }
+            for (int j = 0; j < 32; j += 4) {
+              const float c0 = __uint_as_float(r[j]) - ln_mean, c1 = __uint_as_float(r[j + 1]) - ln_mean;
+              const float c2 = __uint_as_float(r[j + 2]) - ln_mean, c3 = __uint_as_float(r[j + 3]) - ln_mean;
+              q0 = fmaf(c0, c0, q0); q1 = fmaf(c1, c1, q1); q2 = fmaf(c2, c2, q2); q3 = fmaf(c3, c3, q3);
+            }
+            ssq += (q0 + q1) + (q2 + q3);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float c = __uint_as_float(r[j]) - ln_mean; ssq += (j < nrem) ? c * c : 0.f; }
+          }
         }
         ln_rstd = rsqrtf(ssq / (float)d.N + d.ln_eps);
       }
@@ -668,11 +686,17 @@ gemm_tc_tma_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (d.ln_gamma != nullptr) {
-            const int nv = d.N - (col0 + g * 32);
+            // gamma / beta are readable (zero padded) up to the next multiple of 32 columns: vector loads, no predicates
+            const float4* gp = reinterpret_cast<const float4*>(d.ln_gamma + gcol);
+            const float4* bq = reinterpret_cast<const float4*>(d.ln_beta + gcol);
+            const float off = -ln_mean * ln_rstd;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float ga = (j < nv) ? __ldg(d.ln_gamma + gcol + j) : 0.f, be = (j < nv) ? __ldg(d.ln_beta + gcol + j) : 0.f;
-              v[j] = (v[j] - ln_mean) * ln_rstd * ga + be;
+            for (int q = 0; q < 8; ++q) {
+              const float4 ga = __ldg(gp + q), be = __ldg(bq + q);
+              v[4 * q] = fmaf(fmaf(v[4 * q], ln_rstd, off), ga.x, be.x);
+              v[4 * q + 1] = fmaf(fmaf(v[4 * q + 1], ln_rstd, off), ga.y, be.y);
+              v[4 * q + 2] = fmaf(fmaf(v[4 * q + 2], ln_rstd, off), ga.z, be.z);
+              v[4 * q + 3] = fmaf(fmaf(v[4 * q + 3], ln_rstd, off), ga.w, be.w);
             }
           }
           switch (pre_act) {

@@ -177,7 +177,10 @@ static int finalize_impl(dz_seg* s) {
       auto g = b.need(fe + "conv_layers." + std::to_string(l) + ".layer_norm.weight", Co);
       auto be = b.need(fe + "conv_layers." + std::to_string(l) + ".layer_norm.bias", Co);
       if (b.err) return fail(b.err, b.msg);
-      b.ck(upload_vec(s->conv_gamma[l], *g), "conv ln"); b.ck(upload_vec(s->conv_beta[l], *be), "conv ln");
+      // zero padded to a multiple of 32 entries: the fused LayerNorm epilogue of the GEMM reads them with unpredicated vector loads
+      std::vector<float> gp(rup((int)g->size(), 32), 0.f), bp(rup((int)be->size(), 32), 0.f);
+      std::copy(g->begin(), g->end(), gp.begin()); std::copy(be->begin(), be->end(), bp.begin());
+      b.ck(upload_vec(s->conv_gamma[l], gp), "conv ln"); b.ck(upload_vec(s->conv_beta[l], bp), "conv ln");
     }
   }
   const int C6 = a.conv_channels[6];

@@ -71,7 +71,8 @@ typedef struct dz_gemm_desc {
   int64_t res16_plane, res16_bstride;
   int32_t ldr16, res16_row_off;
   /* optional row LayerNorm of the accumulator row (over the N valid columns, biased variance) applied before the activation:
-   * v = (acc - mean) * rstd * ln_gamma[col] + ln_beta[col].  tcgen05 path only, N <= tile width (256), no bias / residual. */
+   * v = (acc - mean) * rstd * ln_gamma[col] + ln_beta[col].  tcgen05 path only, N <= tile width (256), no bias / residual.
+   * Both vectors must be 16-byte aligned and readable, zero padded, up to the next multiple of 32 columns. */
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;

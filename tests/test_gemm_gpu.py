@@ -204,8 +204,10 @@ def test_conv1d_with_fused_layernorm_gelu(npass, B, Tin, Cin, Cout):
     dev, k = "cuda", 3
     x = torch.randn(B, Tin, Cin, device=dev)
     w = torch.randn(Cout, Cin, k, device=dev) / (Cin * k) ** 0.5
-    gamma = 1.0 + 0.2 * torch.randn(Cout, device=dev)
-    beta = 0.3 * torch.randn(Cout, device=dev)
+    gamma = torch.zeros(rup(Cout, 32), device=dev)      # zero padded to a multiple of 32 columns (contract of ln_gamma / ln_beta)
+    beta = torch.zeros(rup(Cout, 32), device=dev)
+    gamma[:Cout] = 1.0 + 0.2 * torch.randn(Cout, device=dev)
+    beta[:Cout] = 0.3 * torch.randn(Cout, device=dev)
     Cp = rup(Cin, 8)
     xp = to_planes(x, Cp)
     wr = torch.zeros(Cout, k, Cp, device=dev)
@@ -225,7 +227,7 @@ def test_conv1d_with_fused_layernorm_gelu(npass, B, Tin, Cin, Cout):
     xv = planes_value(xp, npass)[..., :Cin].permute(0, 2, 1)
     wv = planes_value(wp, npass).reshape(Cout, k, Cp)[:, :, :Cin].permute(0, 2, 1)
     y = torch.nn.functional.conv1d(xv, wv, stride=2).permute(0, 2, 1)
-    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(y, (Cout,), gamma.double(), beta.double(), 1e-5))
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(y, (Cout,), gamma[:Cout].double(), beta[:Cout].double(), 1e-5))
     got = out_b[0].double() + out_b[1].double()
     _check("ln+gelu planes", got[..., :Cout], ref, 3 if npass == 3 else 1)
     assert (out_b[..., Cout:ldo] == 0).all(), "pad columns must be zeroed"
