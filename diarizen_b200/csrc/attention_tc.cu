@@ -524,285 +524,6 @@ __global__ void __launch_bounds__(A_THREADS, 2) attention_tc2_kernel(const __gri
 }
 
 // ================================================================================================
-// v2s: the kernel above with TWO threads per query row (8 softmax warps, 320 threads; see the softmax section)
-// ================================================================================================
-static constexpr int A_THREADS_S = 320;
-
-template <int FP16, int VROW>
-__global__ void __launch_bounds__(A_THREADS_S, 2) attention_tc2s_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a,
-                                                                     const int B) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_align1024(smem_raw);
-  uint8_t* Qs = smem;                              // 128 x 64, SW128
-  uint8_t* Ks = Qs + 16384;                        // KV_STAGES x (64 keys x 64 d)
-  uint8_t* Vs = Ks + KV_STAGES * 8192;             // KV_STAGES x (80 rows x 64 keys): 64 d rows + ones row + 15 zero rows
-  // VROW: V arrives row-major (64 keys x 64 d per stage, MN-major B operand) and the ones column lives in one shared 8 KB
-  // constant block after the stages (second 64-wide N chunk, reached through the descriptor's leading byte offset)
-  constexpr int VST = VROW ? 8192 : V_STAGE_BYTES;
-  constexpr int VTOT = VROW ? KV_STAGES * 8192 + 8192 : KV_STAGES * V_STAGE_BYTES;
-  uint8_t* Vc = Vs + KV_STAGES * 8192;
-  uint8_t* Ps = Vs + VTOT;                         // 2 x (128 x 64), SW128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 16384);
-  uint64_t* q_full = bars;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [3]
-  uint64_t* kv_empty = bars + 5;   // [3]
-  uint64_t* s_full = bars + 8;     // [2]
-  uint64_t* p_ready = bars + 10;   // [2]
-  uint64_t* o_ready = bars + 12;   // one phase per key block
-  uint64_t* o_final = bars + 13;   // one phase per work item
-  uint64_t* o_free = bars + 14;    // one phase per work item (the 4 softmax warps have read O out of TMEM)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
-  float* tab = reinterpret_cast<float*>(bars + 16);  // [2T-1 + 64 pad]
-
-  const int T = a.T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nblk = (T + ABK - 1) / ABK;
-  const int nqt = (T + ABQ - 1) / ABQ;
-  const int n_items = B * a.nheads * nqt;   // item = ((head * B) + window) * nqt + query tile: head-major, so that a
-                                            // persistent CTA keeps its bias table across consecutive items
-  const bool has_bias = a.bias_tab != nullptr;
-
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&p_ready[0], 8); mbar_init(&p_ready[1], 8);
-    mbar_init(o_ready, 1);
-    mbar_init(o_final, 1);
-    mbar_init(o_free, 8);
-    mbar_fence_init();
-    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.vt);
-  }
-  if (warp == 9) tmem_alloc(tmem_ptr, 256);
-  {
-    // constant tail of every V stage: row 64 = ones (swizzle phase 0: stored as is), rows 65..79 = zeros
-    const uint32_t one2 = FP16 ? 0x3C003C00u : 0x3F803F80u;
-    if (VROW) {
-      // row r (key) of the constant block: column 0 = 1, columns 1..63 = 0; column 0 sits in 16-byte chunk (0 ^ (r & 7))
-      for (int i = threadIdx.x; i < 2048; i += A_THREADS_S) {
-        const int r = i >> 5, wd = i & 31;
-        reinterpret_cast<uint32_t*>(Vc)[i] = (wd == ((r & 7) << 2)) ? (one2 & 0xFFFFu) : 0u;
-      }
-    } else {
-      for (int i = threadIdx.x; i < KV_STAGES * 512; i += A_THREADS_S) {
-        const int s = i >> 9, wd = i & 511;
-        reinterpret_cast<uint32_t*>(Vs + s * V_STAGE_BYTES + 8192)[wd] = wd < 32 ? one2 : 0u;
-      }
-    }
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_O = tmem_base + 128;
-
-  if (warp == 8) {
-    if (lane == 0) {
-      uint32_t g = 0, n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        const int qt = it % nqt, pair = it / nqt, b = pair % B, hi = pair / B;
-        if (n > 0) mbar_wait(q_empty, (n - 1) & 1);   // every S = Q K^T of the previous item has completed
-        mbar_expect_tx(q_full, 16384);
-        tma_load_3d(Qs, &maps.q, q_full, a.q_col + hi * 64, qt * ABQ, b);
-        for (int j = 0; j < nblk; ++j, ++g) {
-          const uint32_t s = g % KV_STAGES, use = g / KV_STAGES;
-          if (use > 0) mbar_wait(&kv_empty[s], (use - 1) & 1);
-          mbar_expect_tx(&kv_full[s], 16384);
-          tma_load_3d(Ks + s * 8192, &maps.k, &kv_full[s], a.k_col + hi * 64, j * ABK, b);
-          if (VROW) tma_load_3d(Vs + s * VST, &maps.vt, &kv_full[s], a.v_col + hi * 64, j * ABK, b);
-          else tma_load_3d(Vs + s * VST, &maps.vt, &kv_full[s], j * ABK, hi * 64, b);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 64, FP16);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 80, FP16) | (VROW ? (1u << 16) : 0u);   // bit 16: B is MN-major
-      const uint32_t qa = smem_u32(Qs);
-      uint32_t g = 0, n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        mbar_wait(q_full, n & 1);
-        {
-          const uint32_t s0 = g % KV_STAGES;
-          mbar_wait(&kv_full[s0], (g / KV_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t ka = smem_u32(Ks + s0 * 8192), ts = tmem_base + (g & 1) * 64;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(ts, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, k > 0);
-          umma_commit(&s_full[g & 1]);
-          if (nblk == 1) umma_commit(q_empty);
-        }
-        for (int j = 0; j < nblk; ++j, ++g) {
-          if (j + 1 < nblk) {
-            // S of the next block: its TMEM buffer was last read by the softmax of block g-1, whose p_ready we have observed
-            const uint32_t g1 = g + 1, s1 = g1 % KV_STAGES;
-            mbar_wait(&kv_full[s1], (g1 / KV_STAGES) & 1);
-            tc_fence_after();
-            const uint32_t ka = smem_u32(Ks + s1 * 8192), ts = tmem_base + (g1 & 1) * 64;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(ts, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, k > 0);
-            umma_commit(&s_full[g1 & 1]);
-            if (j + 2 == nblk) umma_commit(q_empty);   // last read of this item's Q tile
-          }
-          const uint32_t s = g % KV_STAGES;
-          mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
-          if (j == 0 && n > 0) mbar_wait(o_free, (n - 1) & 1);   // the previous item's O has been read out of TMEM
-          tc_fence_after();
-          const uint32_t pa = smem_u32(Ps + (g & 1) * 16384), va = smem_u32(Vs + s * VST);
-          if (VROW) {
-            const uint32_t lbo = smem_u32(Vc) - va;   // first N chunk (d 0..63) -> second chunk (ones column + 15 zeros)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)   // 16 keys = 16 rows of 128 B per step
-              umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128_mn(va + k * 2048, lbo), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_O, umma_desc_sw128(pa + k * 32), umma_desc_sw128(va + k * 32), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[s]);
-          umma_commit(o_ready);
-        }
-        umma_commit(o_final);
-      }
-    }
-  } else {
-    // ---------------- softmax warps: TWO threads per query row (warps w and w + 4 share a TMEM lane quarter, each takes 32 of the
-    // 64 key columns of a block): twice the warps in flight for the same work - the ncu capture of the one-thread-per-row kernel
-    // shows it latency-bound (issue slots 43 % busy, 2 softmax warps per scheduler) ----------------
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;  // 0..127
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const int sw = row & 7;
-    uint32_t g = 0, n = 0;
-    int cur_h = -1;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-      const int qt = it % nqt, pair = it / nqt, b = pair % B, hi = pair / B;
-      const int tq = qt * ABQ + row;
-      const bool qvalid = tq < T;
-      const float gate = (has_bias && a.gate != nullptr) ? a.gate[((long long)b * a.nheads + hi) * T + (qvalid ? tq : T - 1)] * LOG2E : 0.f;
-      if (has_bias && hi != cur_h) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done with the previous head's table
-        const float* src = a.bias_tab + (long long)hi * (2 * T - 1);
-        for (int i = threadIdx.x; i < 2 * T - 1 + 64; i += 256) tab[i] = (i < 2 * T - 1) ? src[i] : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_h = hi;
-      }
-      const float* trow = tab + (T - 1) - (qvalid ? tq : T - 1) + 32 * half;  // trow[k] = tab[k - q + T - 1], own column half
-      float m_used = 0.f;   // reference exponent (log2 domain); block 0 always re-references
-      for (int j = 0; j < nblk; ++j, ++g) {
-        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-        tc_fence_after();
-        float r[32];
-        {
-          uint32_t* ru = reinterpret_cast<uint32_t*>(r);
-          tmem_ld_32x32(tmem_base + (g & 1) * 64 + lane_off + 32 * half, ru);
-          tmem_ld_wait();
-        }
-        const int kbase = j * ABK;
-        const float negm = -m_used;
-        if (has_bias) {
-          const float* tr = trow + kbase;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = fmaf(gate, tr[c], fmaf(r[c], LOG2E, negm));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = fmaf(r[c], LOG2E, negm);
-        }
-        if (j == nblk - 1) {
-          const int nvalid = T - kbase - 32 * half;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = (c < nvalid) ? r[c] : -INFINITY;
-        }
-        float mx = fmax3(r[0], r[1], r[2]);
-#pragma unroll
-        for (int c = 3; c + 1 < 32; c += 2) mx = fmax3(mx, r[c], r[c + 1]);
-        mx = fmaxf(mx, r[31]);
-        // row maximum over both column halves: exchanged through this row's slot of the P buffer that is written next (free since
-        // s_full fired: the P V product that last read it was issued before this block's S), 64-thread barrier per lane quarter
-        float* xrow = reinterpret_cast<float*>(Ps + (g & 1) * 16384 + row * 128);
-        xrow[half] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
-        mx = fmaxf(mx, xrow[half ^ 1]);
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");   // both halves have read before either overwrites the row with P
-        // lazy re-referencing: exponentials stay relative to m_used unless the row maximum moved by more than 2^8
-        const bool need = (j == 0) || (mx > 8.0f);
-        if (need) {
-          m_used += mx;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] -= mx;
-        }
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
-          const float corr = need ? ex2(-mx) : 1.0f;
-          mbar_wait(o_ready, (g - 1) & 1);   // P V of the previous block has landed in O
-          tc_fence_after();
-          uint32_t o[32];
-          tmem_ld_32x32(tmem_O + lane_off + half * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * corr);
-          tmem_st_32x32(tmem_O + lane_off + half * 32, o);
-          if (half == 1) {   // the denominator column
-            uint32_t o1[16];
-            tmem_ld_32x32_x16(tmem_O + lane_off + 64, o1);
-            tmem_ld_wait();
-            tmem_st_32x32_x1(tmem_O + lane_off + 64, __float_as_uint(__uint_as_float(o1[0]) * corr));
-          }
-          tmem_st_wait();
-        }
-        uint8_t* prow = Ps + (g & 1) * 16384 + row * 128;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = pack2_16<FP16>(ex2(r[8 * c8 + 2 * e]), ex2(r[8 * c8 + 2 * e + 1]));
-          *reinterpret_cast<uint4*>(prow + (((4 * half + c8) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g & 1]);
-      }
-      mbar_wait(o_final, n & 1);
-      tc_fence_after();
-      uint32_t o[32], o1[16];
-      tmem_ld_32x32(tmem_O + lane_off + half * 32, o);
-      tmem_ld_32x32_x16(tmem_O + lane_off + 64, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      if (qvalid) {
-        const float inv = 1.0f / __uint_as_float(o1[0]);
-        bf16* op = a.out + ((long long)b * T + tq) * a.ldo + hi * 64 + 32 * half;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            bf16 h0, l0, h1, l1;
-            split_bf16(__uint_as_float(o[8 * c8 + 2 * e]) * inv, h0, l0, FP16);
-            split_bf16(__uint_as_float(o[8 * c8 + 2 * e + 1]) * inv, h1, l1, FP16);
-            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          *reinterpret_cast<uint4*>(op + 8 * c8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          if (a.out_planes > 1) *reinterpret_cast<uint4*>(op + a.out_plane + 8 * c8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// ================================================================================================
 // v3: split-precision (bf16x3, fp32-class) variant of the kernel above for the 1e-3 parity mode - until round 2 that mode fell
 // back to the CUDA-core kernel (50 % of its run time).  Operands arrive as bf16 hi + lo planes; both products are
 // accumulated as three tensor-core passes into the same fp32 accumulator:
@@ -1173,20 +894,6 @@ cudaError_t attention_tc_plan_launch(const AttnPlan* p, cudaStream_t st) {
     const long long items = (long long)grid.x * grid.y * grid.z;
     const unsigned g = (unsigned)(items < slots ? items : slots);
     const int variant = (p->a.fp16 ? 1 : 0) | (p->a.v != nullptr ? 2 : 0);
-    static const bool split = [] { const char* e = getenv("DZ_ATTN_ONE_THREAD_PER_ROW"); return !(e && e[0] == '1'); }();
-    if (split && variant >= 2) {   // row-major V (the engine's layout): two threads per query row
-      static size_t attr_s = 0;
-      const size_t smem_s = p->smem;
-      if (smem_s > attr_s) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc2s_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2s_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-        if (e != cudaSuccess) return e;
-        attr_s = smem_s;
-      }
-      if (variant == 3) attention_tc2s_kernel<1, 1><<<g, A_THREADS_S, smem_s, st>>>(p->maps, p->a, p->B);
-      else attention_tc2s_kernel<0, 1><<<g, A_THREADS_S, smem_s, st>>>(p->maps, p->a, p->B);
-      return cudaGetLastError();
-    }
     switch (variant) {
       case 0: attention_tc2_kernel<0, 0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
       case 1: attention_tc2_kernel<1, 0><<<g, A_THREADS, p->smem, st>>>(p->maps, p->a, p->B); break;
