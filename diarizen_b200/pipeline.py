@@ -210,7 +210,7 @@ class DiariZenPipeline:
         self.rttm_out_dir = rttm_out_dir
         self._L = _lib.lib()
         self.last = {}
-        self._tails = {}
+        self._planned = {}
         if not hasattr(self, "_segmentation_mc"):
             self._segmentation_mc = _mc
         # window-sharded mode: fraction of an even window share that the clustering rank takes (None = even split); see
@@ -228,7 +228,7 @@ class DiariZenPipeline:
         self._embedding = self._embedding.to(device)
         self.device = self._segmentation.device
         self.clustering.device = self.device
-        self._tails = {}
+        self._planned = {}
         return self
 
     @property
@@ -305,23 +305,19 @@ class DiariZenPipeline:
         dev, L, S = self.device, self._L, 4
         chunks = wloc.as_strided((max(n_loc, 0), window), (step, 1))
         raw = torch.zeros((per, T, S), device=dev, dtype=torch.uint8)
-        bs = self.engine_windows
-        # The engines plan (workspace + tensor maps) per batch shape: the ragged last batch is padded to the full batch
-        # size instead of triggering a re-plan (two multi-GB reallocations per recording otherwise).
+        bs = self._call_batch("seg", n_loc, self.engine_windows)
+        # The engine plans (workspace + tensor maps) per batch shape: every call of a recording uses ONE batch size (the window
+        # count split evenly over the fewest calls that fit `engine_windows`), the last call zero padded to it.
         for a in range(0, n_loc, bs):
             b = min(a + bs, n_loc)
-            if b - a == bs or n_loc < bs:
+            if b - a == bs:
                 self._segmentation.hard(chunks[a:b].contiguous(), want_logp=False, ml_out=raw[a:b])
             else:
-                # ragged last batch: padded to a planned batch size (bs, or bs / 2 on a second engine instance that keeps its
-                # own plan) - never a re-plan of the main engine
-                rem = b - a
-                eng, pb = (self._tail_engine("seg"), bs // 2) if rem <= bs // 2 else (self._segmentation, bs)
-                wpad = torch.zeros((pb, window), device=dev, dtype=torch.float32)
-                wpad[:rem] = chunks[a:b]
-                tail = torch.empty((pb, T, S), device=dev, dtype=torch.uint8)
-                eng.hard(wpad, want_logp=False, ml_out=tail)
-                raw[a:b] = tail[:rem]
+                wpad = torch.zeros((bs, window), device=dev, dtype=torch.float32)
+                wpad[:b - a] = chunks[a:b]
+                tail = torch.empty((bs, T, S), device=dev, dtype=torch.uint8)
+                self._segmentation.hard(wpad, want_logp=False, ml_out=tail)
+                raw[a:b] = tail[:b - a]
         self._mark("segmentation")
         return (raw,) + self._masks_and_embeddings(raw, wloc, chunks, window, step, T, c0, c1, per)
 
@@ -343,8 +339,8 @@ class DiariZenPipeline:
         same = all(e == i * step for i, e in enumerate(e_starts))
         self._mark("count_masks")
         emb = torch.zeros((per, S, 256), device=dev, dtype=torch.float32)
-        ebs = self.engine_emb_windows
         n_loc = c1 - c0
+        ebs = self._call_batch("emb", n_loc, self.engine_emb_windows)
         for a in range(0, n_loc, ebs):
             b = min(a + ebs, n_loc)
             if same:
@@ -353,15 +349,10 @@ class DiariZenPipeline:
                 wv = torch.stack([torch.nn.functional.pad(wloc[max(e_starts[i], 0):e_starts[i] + window], (0, max(0, e_starts[i] + window - wloc.shape[0])))[:window]
                                   for i in range(a, b)])
             mk = masks[a:b]
-            eng = self._embedding
-            if b - a < ebs and n_loc >= ebs:   # ragged last batch: pad to ebs, or to ebs / 4 on a second engine instance
-                rem = b - a
-                pb = ebs
-                if rem <= ebs // 4 and ebs >= 8:
-                    eng, pb = self._tail_engine("emb"), ebs // 4
-                wv = torch.cat([wv, torch.zeros((pb - rem, window), device=dev, dtype=torch.float32)])
-                mk = torch.cat([mk, torch.zeros((pb - rem, S, T), device=dev, dtype=torch.float32)])
-            emb[a:b] = eng.embed_windows(wv, mk)[:b - a]
+            if b - a < ebs:   # last call: zero padded to the recording's batch size
+                wv = torch.cat([wv, torch.zeros((ebs - (b - a), window), device=dev, dtype=torch.float32)])
+                mk = torch.cat([mk, torch.zeros((ebs - (b - a), S, T), device=dev, dtype=torch.float32)])
+            emb[a:b] = self._embedding.embed_windows(wv, mk)[:b - a]
         self._mark("embedding")
         return seg, stats, emb
 
@@ -403,18 +394,20 @@ class DiariZenPipeline:
         self.last = out
         return out
 
-    def _tail_engine(self, which: str):
-        """second instance of a network engine (same weights) that serves the small ragged last batch of a recording: each
-        instance keeps the plan of ONE batch shape, so neither ever re-plans while recordings of different lengths stream by"""
-        if which not in self._tails:
-            m = self._segmentation if which == "seg" else self._embedding
-            if which == "seg":
-                sd, gi, ai = m._ctor
-                self._tails[which] = SegmentationModel(m.arch, sd, precision=m.precision, gemm_impl=gi, attn_impl=ai, device=self.device)
-            else:
-                sd, precision, gi, prefix = m._ctor
-                self._tails[which] = EmbeddingModel(sd, precision=precision, gemm_impl=gi, device=self.device, prefix=prefix)
-        return self._tails[which]
+    def _call_batch(self, which: str, n: int, cap: int) -> int:
+        """windows per engine call for a run of `n` windows: n split evenly over ceil(n / cap) calls (so that the zero padding
+        of the last call is less than one window per call - with a fixed batch of `cap`, a rank holding 299 of the windows of a
+        sharded recording would pad 37 of them).  The batch the engine is currently planned for is kept when it wastes < 3 %:
+        a re-plan reallocates the workspace."""
+        if n <= 0:
+            return max(1, cap)
+        calls = -(-n // cap)
+        b = -(-n // calls)
+        cur = self._planned.get(which)
+        if cur is not None and cur <= cap and (-(-n // cur) * cur - n) <= 0.03 * n:
+            return cur
+        self._planned[which] = b
+        return b
 
     def _mark(self, name: Optional[str]):
         """stage timer (only with `collect_timing`, which synchronises the device at every stage boundary)"""
