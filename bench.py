@@ -465,11 +465,11 @@ def run_pipeline_bench(args, world, rank, local, dist):
     Cn, Tn = last["num_chunks"], last["num_frames"]
     peaks = measured_peaks()
     # ---- per-launch device times of one engine call of each network (CUDA events around every launch) ----
-    bsz = pipe.engine_windows
+    bsz = pipe._planned.get("seg", pipe.engine_windows)      # windows per engine call the recording actually ran with
     wb = wav_dev[: window].repeat(bsz, 1).contiguous()
     pipe._segmentation.profile(wb)
     seg_prof = pipe._segmentation.profile(wb)
-    ebs = pipe.engine_emb_windows
+    ebs = pipe._planned.get("emb", pipe.engine_emb_windows)
     pipe._embedding.embed_windows(wb[:ebs], torch.ones(ebs, 4, Tn, device="cuda"))
     emb_prof = pipe._embedding.profile()
     n_seg_b, n_emb_b = Cn / bsz, Cn / ebs
