@@ -353,7 +353,7 @@ def device_vb_gmm(X: np.ndarray, Phi: np.ndarray, gamma0: np.ndarray, Fa: float,
     """diarizen/clustering/VBx.py:73-113 (loopProb = 0): both halves of each iteration run on the GPU in float64
     (dz_vbx_model / dz_vbx_resp); the host keeps only the S-vector prior and the scalar ELBO convergence test."""
     L = _lib.lib()
-    dev = torch.device(device if device is not None else "cuda:0")
+    dev = torch.device(device if device is not None else "cuda")
     N, D = X.shape
     S = gamma0.shape[1]
     with torch.cuda.device(dev):
