@@ -25,4 +25,4 @@ for h in (1, 5, 10):
     for _ in range(10): _lib.check(L.dz_attention(C.byref(a), B, 0, None))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"h={h}: {ms*1e3:.1f} us  {4.0*T*T*64*h*B/ms/1e9:.0f} TFLOP/s  split={os.environ.get('DZ_ATTN_ONE_THREAD_PER_ROW','0')!='1'}")
+    print(f"h={h}: {ms*1e3:.1f} us  {4.0*T*T*64*h*B/ms/1e9:.0f} TFLOP/s")
