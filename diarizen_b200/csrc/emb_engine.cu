@@ -420,7 +420,7 @@ int dz_emb_forward(dz_emb* s, const float* wav_dev, const float* masks_dev, int 
   return DZ_OK;
 }
 int dz_emb_last_launches(const dz_emb* s) { return s ? s->last_launches : 0; }
-/* debug: copy the fbank features [B][F][80] (before mean subtraction) of the last forward */
+/* debug: copy the fbank features [B][80][F] (mel-major, before mean subtraction) of the last forward */
 int64_t dz_emb_tap_fbank(dz_emb* s, float* dst_dev, int64_t capacity) {
   if (!s || !s->fb_dev) return fail(DZ_ERR_STATE, "no forward has run");
   const int64_t n = (int64_t)s->B * s->F * 80;

@@ -95,13 +95,14 @@ __global__ void __launch_bounds__(256) fbank_kernel(FbankArgs a) {
     if (k < FB_BINS) P[k] = pw[j];
   }
   __syncwarp();
-  float* dst = a.out + ((long long)b * a.F + f) * 80;
+  // mel-major output [b][mel][frame]: the consumers (mean over frames, 3x3 conv over (mel, frame)) walk along frames
+  float* dst = a.out + (long long)b * 80 * a.F + f;
   for (int m = lane; m < 80; m += 32) {
     const int ks = a.mel_range[2 * m], ke = a.mel_range[2 * m + 1];
     const float* wrow = a.mel_w + m * FB_BINS;
     float acc = 0.f;
     for (int k = ks; k < ke; ++k) acc = fmaf(P[k], __ldg(wrow + k), acc);
-    dst[m] = logf(fmaxf(acc, 1.1920928955078125e-07f));
+    dst[(long long)m * a.F] = logf(fmaxf(acc, 1.1920928955078125e-07f));
   }
 }
 
@@ -112,17 +113,19 @@ cudaError_t launch_fbank(const FbankArgs& a, int B, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// per (window, mel) mean over frames
-__global__ void fbank_mean_kernel(const float* __restrict__ fb, int F, float* __restrict__ mean) {
-  const int b = blockIdx.x, m = threadIdx.x;  // 80 threads
-  if (m >= 80) return;
-  const float* p = fb + (long long)b * F * 80 + m;
+// per (window, mel) mean over frames: one warp per contiguous row of the mel-major features.  Lane l sums frames l, l + 32, ...
+// in order and the 32 partial sums are combined by the shuffle tree (fp32; the reference's torch.mean uses another order).
+__global__ void __launch_bounds__(256) fbank_mean_kernel(const float* __restrict__ fb, int rows, int F, float* __restrict__ mean) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* p = fb + (long long)r * F;
   float s = 0.f;
-  for (int f = 0; f < F; ++f) s += p[(long long)f * 80];
-  mean[b * 80 + m] = s / F;
+  for (int f = lane; f < F; f += 32) s += p[f];
+  s = warp_sum(s);
+  if (lane == 0) mean[r] = s / F;
 }
 cudaError_t launch_fbank_mean(const float* fb, int B, int F, float* mean, cudaStream_t st) {
-  fbank_mean_kernel<<<B, 96, 0, st>>>(fb, F, mean);
+  fbank_mean_kernel<<<(B * 80 + 7) / 8, 256, 0, st>>>(fb, B * 80, F, mean);
   return cudaGetLastError();
 }
 
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) emb_conv1_kernel(Conv1Args a) {
       for (int kw = 0; kw < 3; ++kw) {
         const int hh = h + kh - 1, ww = wf + kw - 1;
         float v = 0.f;
-        if (hh >= 0 && hh < 80 && ww >= 0 && ww < a.F) v = a.fb[((long long)b * a.F + ww) * 80 + hh] - a.mean[b * 80 + hh];
+        if (hh >= 0 && hh < 80 && ww >= 0 && ww < a.F) v = a.fb[((long long)b * 80 + hh) * a.F + ww] - a.mean[b * 80 + hh];
         in[kh * 3 + kw] = v;
       }
     bf16* o = a.out + (((long long)b * 80 + h) * (a.F + 2) + wf + 1) * 32;

@@ -12,7 +12,7 @@ struct FbankArgs {
   const float* window;      // [400] hamming
   const float* mel_w;       // [80][257]
   const int* mel_range;     // [80][2] first / one-past-last non-zero FFT bin
-  float* out;               // [B][F][80] log-mel (before mean subtraction)
+  float* out;               // [B][80][F] log-mel, mel-major (before mean subtraction)
 };
 struct Conv1Args {
   const float* fb; const float* mean; int B; int F;

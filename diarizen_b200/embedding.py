@@ -87,7 +87,7 @@ class EmbeddingModel:
         _lib.check(n)
         out = torch.empty(n, device=self.device, dtype=torch.float32)
         _lib.check(self._L.dz_emb_tap_fbank(self._h, C.c_void_p(out.data_ptr()), n))
-        return out.view(-1, self._L.dz_emb_num_fbank_frames(self._keep[0].shape[1]), 80)
+        return out.view(-1, 80, self._L.dz_emb_num_fbank_frames(self._keep[0].shape[1])).transpose(1, 2)   # the engine keeps them mel-major
 
     def profile(self):
         n = self._L.dz_emb_num_steps(self._h)
