@@ -134,8 +134,7 @@ cudaError_t launch_fbank_mean(const float* fb, int B, int F, float* mean, cudaSt
 // [b][h = mel][1 + w = frame][32].  One thread per output pixel, 32 channels.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) emb_conv1_kernel(Conv1Args a) {
-  __shared__ __align__(16) float w[9 * 32];
-  __shared__ float sc[32], sh[32];
+  __shared__ float w[9 * 32], sc[32], sh[32];
   for (int i = threadIdx.x; i < 288; i += blockDim.x) {
     const int c = i / 9, t = i - c * 9;
     w[t * 32 + c] = a.w[i];   // [tap][c]
@@ -160,24 +159,21 @@ __global__ void __launch_bounds__(256) emb_conv1_kernel(Conv1Args a) {
     bf16* o = a.out + (((long long)b * 80 + h) * (a.F + 2) + wf + 1) * 32;
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
-      // 8 output channels at a time: the tap weights come as two 16-byte shared-memory loads per tap (one 4-byte load per FMA before)
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w + t * 32 + c8 * 8), w1 = *reinterpret_cast<const float4*>(w + t * 32 + c8 * 8 + 4);
-        acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]); acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
-        acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]); acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
-      }
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int c = c8 * 8 + e * 2;
-        const float v0 = fmaxf(acc[2 * e] * sc[c] + sh[c], 0.f), v1 = fmaxf(acc[2 * e + 1] * sc[c + 1] + sh[c + 1], 0.f);
+        float v2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = c8 * 8 + e * 2 + q;
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc = fmaf(in[t], w[t * 32 + c], acc);
+          v2[q] = fmaxf(acc * sc[c] + sh[c], 0.f);
+        }
         bf16 h0, l0, h1, l1;
-        split_bf16(v0, h0, l0, a.fp16);
-        split_bf16(v1, h1, l1, a.fp16);
+        split_bf16(v2[0], h0, l0, a.fp16);
+        split_bf16(v2[1], h1, l1, a.fp16);
         hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
         lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
       }
