@@ -192,6 +192,7 @@ def lib() -> C.CDLL:
         "dz_reconstruct": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
         "dz_pdist": [vp, i32, i32, vp, vp],
         "dz_linkage_centroid": [vp, i32, vp, vp, vp],
+        "dz_linkage_centroid_variant": [vp, i32, vp, vp, vp, i32],
         "dz_assign": [vp, i32, i32, i32, vp, vp],
         "dz_conv3x3": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
         "dz_dendrogram_cut": [vp, i32, C.c_double, i32, i32, i32, i32, i32, vp, vp, vp, vp],
@@ -223,5 +224,5 @@ EXPORTS = [
     "dz_emb_create", "dz_emb_destroy", "dz_emb_set_param", "dz_emb_finalize", "dz_emb_num_fbank_frames", "dz_emb_forward",
     "dz_emb_last_launches", "dz_emb_tap_fbank", "dz_emb_num_steps", "dz_emb_profile",
     "dz_median_filter", "dz_speaker_count", "dz_embedding_masks", "dz_reconstruct", "dz_pdist", "dz_linkage_workspace_bytes",
-    "dz_conv3x3", "dz_linkage_centroid", "dz_dendrogram_cut_workspace_bytes", "dz_dendrogram_cut", "dz_assign", "dz_vbx_model", "dz_vbx_resp",
+    "dz_conv3x3", "dz_linkage_centroid", "dz_linkage_centroid_variant", "dz_dendrogram_cut_workspace_bytes", "dz_dendrogram_cut", "dz_assign", "dz_vbx_model", "dz_vbx_resp",
 ]

@@ -153,7 +153,7 @@ class DeviceDendrogram:
     merge loop (dz_linkage_centroid, bit-identical to scipy.cluster.hierarchy.linkage(method="centroid")), and the
     flat-cluster selection (dz_dendrogram_cut).  Only the N labels and eight counters come back to the host."""
 
-    def __init__(self, unit_embeddings: np.ndarray, device=None):
+    def __init__(self, unit_embeddings: np.ndarray, device=None, variant: int = 0):
         L = _lib.lib()
         self.device = torch.device(device if device is not None else "cuda")
         x = torch.as_tensor(np.ascontiguousarray(unit_embeddings, dtype=np.float32), device=self.device)
@@ -165,7 +165,9 @@ class DeviceDendrogram:
         with torch.cuda.device(self.device):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(L.dz_pdist(C.c_void_p(x.data_ptr()), N, D, C.c_void_p(dist.data_ptr()), st))
-            _lib.check(L.dz_linkage_centroid(C.c_void_p(dist.data_ptr()), N, C.c_void_p(self._Z.data_ptr()), C.c_void_p(ws.data_ptr()), st))
+            _lib.check(L.dz_linkage_centroid_variant(C.c_void_p(dist.data_ptr()), N, C.c_void_p(self._Z.data_ptr()), C.c_void_p(ws.data_ptr()), st,
+                                                     int(variant)))
+        self.row_rescans = int(ws[24 * N:24 * N + 8].view(torch.int64).item()) if variant != 1 else None   # lazy-kernel counter
 
     def Z(self) -> np.ndarray:
         """scipy-layout linkage matrix (N-1, 4) float64 on the host."""
@@ -189,9 +191,9 @@ class DeviceDendrogram:
                                       "num_large_at_threshold": int(i[4]), "target": int(i[5])}
 
 
-def device_linkage_centroid(unit_embeddings: np.ndarray, device=None) -> np.ndarray:
+def device_linkage_centroid(unit_embeddings: np.ndarray, device=None, variant: int = 0) -> np.ndarray:
     """scipy linkage(method="centroid", metric="euclidean") on the GPU -> Z (N-1, 4) float64."""
-    return DeviceDendrogram(unit_embeddings, device).Z()
+    return DeviceDendrogram(unit_embeddings, device, variant).Z()
 
 
 def device_assign(soft: np.ndarray, device=None) -> np.ndarray:

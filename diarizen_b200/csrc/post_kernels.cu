@@ -326,27 +326,24 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(double* __restri
   }
 }
 
-// v2 of the merge loop (opt-in, DZ_LINKAGE_V2=1, until it has been checked bit-for-bit against scipy on hardware): the same
-// arithmetic and tie-breaking, but (a) size / nn / nnd / todo live in shared memory instead of L2, (b) the nearest neighbour
-// of the merged cluster y is the block-argmin of the distances the update loop has just computed, so row y is not re-read,
-// (c) the remaining rescans keep four loads in flight per lane.
-__global__ void __launch_bounds__(1024) linkage_centroid_kernel_v2(double* __restrict__ Dm, int N, double* __restrict__ Z,
-                                                                   int* __restrict__ cid) {
-  extern __shared__ double lsm[];
-  double* nnd = lsm;                                   // [N]
-  int* nn = reinterpret_cast<int*>(nnd + N);           // [N]
-  int* size = nn + N;                                  // [N]
-  int* todo = size + N;                                // [N]
-  __shared__ ArgMin sc[32];
-  __shared__ int s_ntodo;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  for (int i = tid; i < N; i += nt) { size[i] = 1; cid[i] = i; }
-  __syncthreads();
-  for (int i = tid >> 5; i < N; i += nt >> 5) {
+// Initial nearest neighbours for every row, on all SMs (one warp per row): the N x N float64 matrix is read once at HBM
+// speed here instead of through the single SM that runs the merge loop. Ties go to the lowest column index.
+__global__ void __launch_bounds__(256) linkage_nn_init_kernel(const double* __restrict__ Dm, int N, int* __restrict__ nn,
+                                                              double* __restrict__ nnd) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < N; i += gridDim.x * wpb) {
     ArgMin best{INFINITY, 0x7fffffff};
     const double* row = Dm + (long long)i * N;
-    for (int j = lane; j < N; j += 32)
-      if (j != i) best = amin(best, ArgMin{row[j], j});
+    for (int j0 = lane; j0 < N; j0 += 256) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u; v[u] = (j < N) ? __ldcs(row + j) : INFINITY; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + 32 * u;
+        if (j < N && j != i) best = amin(best, ArgMin{v[u], j});
+      }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, best.v, o); t.i = __shfl_xor_sync(0xffffffffu, best.i, o);
@@ -354,95 +351,131 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel_v2(double* __res
     }
     if (lane == 0) { nn[i] = best.i; nnd[i] = best.v; }
   }
+}
+
+// The default merge loop (DZ_LINKAGE_V1=1 selects the kernel above): the same arithmetic, the same (distance, index)
+// order for the closest pair, organised for one SM's latency and float64 budget:
+//  * state (nnd, nn, size, the compact list of live slots and its inverse) in shared memory as 8 + 4 x 2 bytes per slot
+//    (N <= ~14 000; beyond that the same code runs on the global workspace); initial neighbours from linkage_nn_init_kernel;
+//  * only LIVE slots are visited: the update loop and the row scans walk the compact list, so a step costs O(live), not O(N)
+//    (the update is float64-issue-bound: two multiplies, a divide and a square root per live slot);
+//  * nnd[z] is a LOWER BOUND when nn[z] == STALE: a row whose cached neighbour was merged away is rescanned only when its
+//    bound reaches the top of the selection (the way scipy's own generic algorithm defers its find_min_dist), and not at
+//    all if a later merge lands below the bound first - `nd < nnd[z]` then makes the row exact again.  The closest pair
+//    is still the exact global minimum with the lowest slot index: every row ordered before it is exact or gets rescanned;
+//  * global round trips are batched: all (d(x,z), d(y,z)) pairs of a batch are loaded before the first store (the stores
+//    to Dm would otherwise fence each iteration's loads behind the previous one's), row scans keep U loads in flight per
+//    thread, d(x,y) is the cached nnd[x], the merged row's neighbour is the block-argmin of the freshly computed distances.
+constexpr uint16_t kStale = 0xFFFFu;
+template <int NT, int U, bool SMEM>
+__global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __restrict__ Dm, int N, double* __restrict__ Z,
+                                                                   int* __restrict__ cid, const int* __restrict__ nn0,
+                                                                   double* __restrict__ nnd0, uint16_t* __restrict__ g16,
+                                                                   unsigned long long* __restrict__ counters) {
+  extern __shared__ double lsm[];
+  double* nnd = SMEM ? lsm : nnd0;                                         // [N]
+  uint16_t* nn = SMEM ? reinterpret_cast<uint16_t*>(lsm + N) : g16;        // [N]
+  uint16_t* size = nn + N;                                                 // [N]
+  uint16_t* live = size + N;                                               // [N] compact list of live slots
+  uint16_t* pos = live + N;                                                // [N] slot -> position in live
+  __shared__ ArgMin sc[32];
+  const int tid = threadIdx.x, nt = NT;
+  for (int i = tid; i < N; i += nt) {
+    size[i] = 1; cid[i] = i; live[i] = (uint16_t)i; pos[i] = (uint16_t)i;
+    nn[i] = (uint16_t)nn0[i];
+    if (SMEM) nnd[i] = nnd0[i];
+  }
   __syncthreads();
+  unsigned long long nrescan = 0;
   for (int step = 0; step < N - 1; ++step) {
-    ArgMin best{INFINITY, 0x7fffffff};
-    for (int i = tid; i < N; i += nt)
-      if (size[i] > 0) best = amin(best, ArgMin{nnd[i], i});
-    best = block_argmin(best, sc);
+    const int L = N - step;                                                // live slots
+    // 1. closest pair: argmin of the bounds; a stale row at the top is made exact and the selection repeats
+    ArgMin best;
+    for (;;) {
+      best = ArgMin{INFINITY, 0x7fffffff};
+      for (int k = tid; k < L; k += nt) { const int i = live[k]; best = amin(best, ArgMin{nnd[i], i}); }
+      best = block_argmin(best, sc);
+      if (nn[best.i] != kStale) break;
+      const int i = best.i;
+      const double* row = Dm + (long long)i * N;
+      ArgMin b2{INFINITY, 0x7fffffff};
+      for (int k0 = tid; k0 < L; k0 += U * nt) {
+        double v[U];
+        int jj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = k0 + u * nt;
+          int j = (k < L) ? (int)live[k] : -1;
+          if (j == i) j = -1;
+          jj[u] = j;
+          v[u] = (j >= 0) ? row[j] : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (jj[u] >= 0) b2 = amin(b2, ArgMin{v[u], jj[u]});
+      }
+      b2 = block_argmin(b2, sc);
+      if (tid == 0) { nn[i] = (uint16_t)b2.i; nnd[i] = b2.v; ++nrescan; }
+      __syncthreads();
+    }
     int x = best.i, y = nn[x];
     if (x > y) { const int t = x; x = y; y = t; }
-    const double dxy = Dm[(long long)x * N + y];
+    const double dxy = best.v;                         // == Dm[x][y]: an exact nnd caches exactly the stored distance
     const int nx = size[x], ny = size[y];
-    __syncthreads();
-    if (tid == 0) {
+    if (tid == nt - 1) {                               // the last warp has the fewest columns: it writes the Z row
       const int ix = cid[x], iy = cid[y];
       Z[step * 4 + 0] = (double)min(ix, iy);
       Z[step * 4 + 1] = (double)max(ix, iy);
       Z[step * 4 + 2] = dxy;
       Z[step * 4 + 3] = (double)(nx + ny);
-      s_ntodo = 0;
+      cid[y] = N + step;
     }
-    __syncthreads();
+    // 2. Lance-Williams update of row / column y over the live slots; x dies
     const double nxy = (double)(nx + ny);
     const double cxy = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dxy), dxy), nxy);
+    const double* rx = Dm + (long long)x * N;
+    double* ry = Dm + (long long)y * N;
     ArgMin ybest{INFINITY, 0x7fffffff};
-    for (int z = tid; z < N; z += nt) {
-      if (size[z] == 0 || z == x || z == y) continue;
-      const double dxz = Dm[(long long)x * N + z], dyz = Dm[(long long)y * N + z];
-      const double t1 = __dmul_rn(__dmul_rn((double)nx, dxz), dxz);
-      const double t2 = __dmul_rn(__dmul_rn((double)ny, dyz), dyz);
-      const double nd = __dsqrt_rn(__ddiv_rn(__dsub_rn(__dadd_rn(t1, t2), cxy), nxy));
-      Dm[(long long)y * N + z] = nd;
-      Dm[(long long)z * N + y] = nd;
-      ybest = amin(ybest, ArgMin{nd, z});
-      const int nz = nn[z];
-      if (nz == x || nz == y) {
-        todo[atomicAdd(&s_ntodo, 1)] = z;
-      } else if (nd < nnd[z]) {
-        nn[z] = y; nnd[z] = nd;
+    for (int k0 = tid; k0 < L; k0 += U * nt) {
+      double dx[U], dy[U];
+      int zz[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * nt;
+        int z = (k < L) ? (int)live[k] : -1;
+        if (z == x || z == y) z = -1;
+        zz[u] = z;
+        dx[u] = (z >= 0) ? rx[z] : 0.0;
+        dy[u] = (z >= 0) ? ry[z] : 0.0;
       }
-    }
-    ybest = block_argmin(ybest, sc);   // = the rescan of row y in v1: min over live z of (d(y,z), z), lowest z on ties
-    if (tid == 0) { size[x] = 0; size[y] = nx + ny; cid[y] = N + step; nn[y] = ybest.i; nnd[y] = ybest.v; }
-    __syncthreads();
-    const int ntodo = s_ntodo;
-    if (ntodo <= 12) {
-      // few rows to rescan (the common case): the WHOLE block scans each of them - one batch of loads in flight per thread
-      // instead of ~N/128 dependent L2 round trips of a single warp; same candidates, same (distance, index) order
-      for (int q = 0; q < ntodo; ++q) {
-        const int i = todo[q];
-        const double* row = Dm + (long long)i * N;
-        ArgMin b2{INFINITY, 0x7fffffff};
-        for (int j0 = tid; j0 < N; j0 += 8 * nt) {
-          double v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { const int j = j0 + u * nt; v[u] = (j < N) ? row[j] : INFINITY; }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + u * nt;
-            if (j < N && j != i && size[j] > 0) b2 = amin(b2, ArgMin{v[u], j});
-          }
-        }
-        b2 = block_argmin(b2, sc);
-        if (tid == 0) { nn[i] = b2.i; nnd[i] = b2.v; }
-      }
-      __syncthreads();
-      continue;
-    }
-    for (int q = tid >> 5; q < ntodo; q += nt >> 5) {
-      const int i = todo[q];
-      ArgMin b2{INFINITY, 0x7fffffff};
-      const double* row = Dm + (long long)i * N;
-      for (int j0 = lane; j0 < N; j0 += 128) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u; v[u] = (j < N) ? row[j] : INFINITY; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 32 * u;
-          if (j < N && j != i && size[j] > 0) b2 = amin(b2, ArgMin{v[u], j});
+      for (int u = 0; u < U; ++u) {
+        const int z = zz[u];
+        if (z < 0) continue;
+        const double t1 = __dmul_rn(__dmul_rn((double)nx, dx[u]), dx[u]);
+        const double t2 = __dmul_rn(__dmul_rn((double)ny, dy[u]), dy[u]);
+        const double nd = __dsqrt_rn(__ddiv_rn(__dsub_rn(__dadd_rn(t1, t2), cxy), nxy));
+        ry[z] = nd;
+        Dm[(long long)z * N + y] = nd;
+        ybest = amin(ybest, ArgMin{nd, z});
+        const int nz = nn[z];
+        if (nd < nnd[z]) {                             // below the row's minimum (or its bound): exact again
+          nn[z] = (uint16_t)y; nnd[z] = nd;
+        } else if (nz == x || nz == y) {
+          nn[z] = kStale;                              // cached neighbour gone: nnd[z] stays as a lower bound
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, b2.v, o); t.i = __shfl_xor_sync(0xffffffffu, b2.i, o);
-        b2 = amin(b2, t);
-      }
-      if (lane == 0) { nn[i] = b2.i; nnd[i] = b2.v; }
+    }
+    ybest = block_argmin(ybest, sc);   // the merged row's neighbour: min over live z of (d(y,z), z), lowest z on ties
+    if (tid == 0) {
+      size[x] = 0; size[y] = (uint16_t)(nx + ny);
+      nn[y] = (uint16_t)ybest.i; nnd[y] = ybest.v;
+      const int p = pos[x], last = live[L - 1];        // drop x from the live list
+      live[p] = (uint16_t)last; pos[last] = (uint16_t)p;
     }
     __syncthreads();
   }
+  if (tid == 0 && counters) counters[0] = nrescan;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,30 +548,43 @@ int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream) {
 }
 /* workspace_dev: at least dz_linkage_workspace_bytes(N) bytes */
 int64_t dz_linkage_workspace_bytes(int N) { return (int64_t)N * (4 * 4 + 8) + 256; }
-int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream) {
-  if (!dist_dev || !z_dev || !workspace_dev || N < 2) return fail(DZ_ERR_INVALID, "bad argument");
+/* variant: 0 = the default choice, 1 = first-generation kernel, 2 = lazy kernel with its state in the global workspace (what
+   N > ~14 000 runs) - 1 and 2 exist so that the tests can drive every code path at small N */
+int dz_linkage_centroid_variant(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream, int variant) {
+  if (!dist_dev || !z_dev || !workspace_dev || N < 2 || variant < 0 || variant > 2) return fail(DZ_ERR_INVALID, "bad argument");
   char* w = (char*)workspace_dev;
   double* nnd = (double*)w; w += (size_t)N * 8;
-  int* size = (int*)w; w += (size_t)N * 4;
   int* cid = (int*)w; w += (size_t)N * 4;
   int* nn = (int*)w; w += (size_t)N * 4;
-  int* todo = (int*)w;
-  static const bool v2 = [] { const char* e = getenv("DZ_LINKAGE_V1"); return !(e && e[0] == '1'); }();
-  const size_t smem = (size_t)N * (8 + 3 * 4);
-  if (v2 && smem <= 200 * 1024) {
+  char* rest = w;                                          // 8 N bytes: v1's size + todo, or the lazy kernel's 16-bit state
+  unsigned long long* counters = (unsigned long long*)(rest + (size_t)N * 8);   // in the 256-byte tail: [0] = row rescans of the last call
+  static const bool env_v1 = [] { const char* e = getenv("DZ_LINKAGE_V1"); return e && e[0] == '1'; }();
+  const bool v1 = variant == 1 || (variant == 0 && env_v1);
+  if (!v1 && N < 65535) {
+    const size_t smem = (size_t)N * (8 + 4 * 2);
+    const bool in_smem = smem <= 220 * 1024 && variant != 2;
+    // 512 threads x 16 loads in flight: ~10 % faster than 1024 x 8 on every data set tried (cheaper barriers, no spills)
+    auto kern = in_smem ? linkage_centroid_lazy_kernel<512, 16, true> : linkage_centroid_lazy_kernel<512, 16, false>;
     static size_t attr = 0;
-    if (smem > attr) {
-      cudaError_t e = cudaFuncSetAttribute(linkage_centroid_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (in_smem && smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(DZ_ERR_CUDA, cudaGetErrorString(e));
       attr = smem;
     }
-    linkage_centroid_kernel_v2<<<1, 1024, smem, (cudaStream_t)stream>>>(dist_dev, N, z_dev, cid);
+    linkage_nn_init_kernel<<<min((N + 7) / 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(dist_dev, N, nn, nnd);
+    CK_LAUNCH();
+    kern<<<1, 512, in_smem ? smem : 0, (cudaStream_t)stream>>>(dist_dev, N, z_dev, cid, nn, nnd, (uint16_t*)rest, counters);
     CK_LAUNCH();
     return DZ_OK;
   }
+  int* size = (int*)rest;
+  int* todo = size + N;
   linkage_centroid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist_dev, N, z_dev, size, cid, nn, nnd, todo);
   CK_LAUNCH();
   return DZ_OK;
+}
+int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream) {
+  return dz_linkage_centroid_variant(dist_dev, N, z_dev, workspace_dev, stream, 0);
 }
 int dz_assign(const double* soft_dev, int C, int S, int K, int8_t* hard_dev, void* stream) {
   if (!soft_dev || !hard_dev || S < 1 || S > 4 || K < 1 || K > 127) return fail(DZ_ERR_INVALID, "bad argument (S <= 4, K <= 127: labels are int8)");

@@ -220,6 +220,8 @@ int dz_pdist(const float* x_dev, int N, int D, double* out_dev, void* stream);
 /* scipy linkage(method="centroid") from the distance matrix (destroyed); Z [N-1][4] float64 */
 int64_t dz_linkage_workspace_bytes(int N);
 int dz_linkage_centroid(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream);
+/* the same with the kernel chosen explicitly (tests): 0 default, 1 first-generation loop, 2 lazy loop with global-memory state */
+int dz_linkage_centroid_variant(double* dist_dev, int N, double* z_dev, void* workspace_dev, void* stream, int variant);
 /* Unit-test surface of the stride-1 3x3 convolution kernels of the embedding trunk (conv3x3_c32.cu: C = 32 / 64 with resident
  * weights; conv3x3_c128.cu: C = 128 with streamed weights).  in / out / res: zero-bordered NHWC 16-bit planes [B][H][W+2][C];
  * w: [C][ldw] with element (kh, kw, ci) at kh * rup(3C, 64) + kw * C + ci; out = relu(conv(in) + bias + res). */

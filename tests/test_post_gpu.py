@@ -101,6 +101,35 @@ def test_linkage_matches_scipy_bitwise(n, seed):
     assert np.array_equal(Z[:, 2], Zref[:, 2]), f"heights differ by {np.abs(Z[:, 2] - Zref[:, 2]).max():.3e}"
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("noise", [0.05, 0.35, 10.0])
+def test_linkage_variants_and_data_shapes(variant, noise):
+    """Every merge-loop variant (default lazy loop with shared-memory state, first-generation loop, lazy loop on the global
+    workspace = what N > 14 000 runs) on tight clusters, overlapping clusters (every merge invalidates many cached neighbours:
+    the case that needs the lazy rescans) and structureless data: Z bit-identical to scipy."""
+    from scipy.cluster.hierarchy import linkage
+    from diarizen_b200.clustering import device_linkage_centroid
+    rng = np.random.default_rng(int(noise * 100) + variant)
+    n = 1500
+    x = rng.standard_normal((6, 256))[rng.integers(0, 6, n)] + noise * rng.standard_normal((n, 256))
+    x = (x / np.linalg.norm(x, axis=-1, keepdims=True)).astype(np.float32)
+    Zref = linkage(x.astype(np.float64), method="centroid", metric="euclidean")
+    Z = device_linkage_centroid(x, variant=variant)
+    assert np.array_equal(Z, Zref)
+
+
+def test_linkage_lazy_rescans_are_bounded():
+    """The lazy loop rescans a row only when its bound reaches the top of the selection: a few rows per merge even on data where
+    the eager variant rescanned hundreds (round-2 measurement: 1.9 per merge at N = 8964 on overlapping clusters)."""
+    from diarizen_b200.clustering import DeviceDendrogram
+    rng = np.random.default_rng(77)
+    n = 3000
+    x = rng.standard_normal((6, 256))[rng.integers(0, 6, n)] + 0.35 * rng.standard_normal((n, 256))
+    x = (x / np.linalg.norm(x, axis=-1, keepdims=True)).astype(np.float32)
+    d = DeviceDendrogram(x)
+    assert 0 <= d.row_rescans <= 4 * n, d.row_rescans
+
+
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 7, 12, 31, 40, 127])
 def test_assign_matches_hungarian(K):
     """dz_assign == scipy.optimize.linear_sum_assignment(maximize=True) per chunk, INCLUDING the tie patterns of the pipeline:
