@@ -353,6 +353,30 @@ __global__ void __launch_bounds__(256) linkage_nn_init_kernel(const double* __re
   }
 }
 
+// two block-wide argmins behind one pair of barriers
+DZ_DEVINL void block_argmin2(ArgMin& a, ArgMin& b, ArgMin* sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, a.v, o); t.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = amin(a, t);
+    ArgMin u; u.v = __shfl_xor_sync(0xffffffffu, b.v, o); u.i = __shfl_xor_sync(0xffffffffu, b.i, o);
+    b = amin(b, u);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) { sc[w] = a; sc[32 + w] = b; }
+  __syncthreads();
+  a = (l < nw) ? sc[l] : ArgMin{INFINITY, 0x7fffffff};
+  b = (l < nw) ? sc[32 + l] : ArgMin{INFINITY, 0x7fffffff};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMin t; t.v = __shfl_xor_sync(0xffffffffu, a.v, o); t.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = amin(a, t);
+    ArgMin u; u.v = __shfl_xor_sync(0xffffffffu, b.v, o); u.i = __shfl_xor_sync(0xffffffffu, b.i, o);
+    b = amin(b, u);
+  }
+}
+
 // The default merge loop (DZ_LINKAGE_V1=1 selects the kernel above): the same arithmetic, the same (distance, index)
 // order for the closest pair, organised for one SM's latency and float64 budget:
 //  * state (nnd, nn, size, the compact list of live slots and its inverse) in shared memory as 8 + 4 x 2 bytes per slot
@@ -365,7 +389,9 @@ __global__ void __launch_bounds__(256) linkage_nn_init_kernel(const double* __re
 //    is still the exact global minimum with the lowest slot index: every row ordered before it is exact or gets rescanned;
 //  * global round trips are batched: all (d(x,z), d(y,z)) pairs of a batch are loaded before the first store (the stores
 //    to Dm would otherwise fence each iteration's loads behind the previous one's), row scans keep U loads in flight per
-//    thread, d(x,y) is the cached nnd[x], the merged row's neighbour is the block-argmin of the freshly computed distances.
+//    thread, d(x,y) is the cached nnd[x], the merged row's neighbour is the block-argmin of the freshly computed distances;
+//  * the update loop also carries the minimum of the (updated) bounds of the rows it visits, so the NEXT step's selection is
+//    ready after the same pair of barriers; a separate selection pass runs only after a rescan.
 constexpr uint16_t kStale = 0xFFFFu;
 template <int NT, int U, bool SMEM>
 __global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __restrict__ Dm, int N, double* __restrict__ Z,
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __res
   uint16_t* size = nn + N;                                                 // [N]
   uint16_t* live = size + N;                                               // [N] compact list of live slots
   uint16_t* pos = live + N;                                                // [N] slot -> position in live
-  __shared__ ArgMin sc[32];
+  __shared__ ArgMin sc[64];
   const int tid = threadIdx.x, nt = NT;
   for (int i = tid; i < N; i += nt) {
     size[i] = 1; cid[i] = i; live[i] = (uint16_t)i; pos[i] = (uint16_t)i;
@@ -387,14 +413,18 @@ __global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __res
   }
   __syncthreads();
   unsigned long long nrescan = 0;
+  ArgMin best{INFINITY, 0x7fffffff};
+  bool have_best = false;                                                  // best = the selection carried over from the last update
   for (int step = 0; step < N - 1; ++step) {
     const int L = N - step;                                                // live slots
     // 1. closest pair: argmin of the bounds; a stale row at the top is made exact and the selection repeats
-    ArgMin best;
     for (;;) {
-      best = ArgMin{INFINITY, 0x7fffffff};
-      for (int k = tid; k < L; k += nt) { const int i = live[k]; best = amin(best, ArgMin{nnd[i], i}); }
-      best = block_argmin(best, sc);
+      if (!have_best) {
+        best = ArgMin{INFINITY, 0x7fffffff};
+        for (int k = tid; k < L; k += nt) { const int i = live[k]; best = amin(best, ArgMin{nnd[i], i}); }
+        best = block_argmin(best, sc);
+      }
+      have_best = false;
       if (nn[best.i] != kStale) break;
       const int i = best.i;
       const double* row = Dm + (long long)i * N;
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __res
     const double cxy = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dxy), dxy), nxy);
     const double* rx = Dm + (long long)x * N;
     double* ry = Dm + (long long)y * N;
-    ArgMin ybest{INFINITY, 0x7fffffff};
+    ArgMin ybest{INFINITY, 0x7fffffff}, obest{INFINITY, 0x7fffffff};
     for (int k0 = tid; k0 < L; k0 += U * nt) {
       double dx[U], dy[U];
       int zz[U];
@@ -459,14 +489,19 @@ __global__ void __launch_bounds__(NT) linkage_centroid_lazy_kernel(double* __res
         Dm[(long long)z * N + y] = nd;
         ybest = amin(ybest, ArgMin{nd, z});
         const int nz = nn[z];
-        if (nd < nnd[z]) {                             // below the row's minimum (or its bound): exact again
-          nn[z] = (uint16_t)y; nnd[z] = nd;
+        double bound = nnd[z];
+        if (nd < bound) {                              // below the row's minimum (or its bound): exact again
+          nn[z] = (uint16_t)y; nnd[z] = nd; bound = nd;
         } else if (nz == x || nz == y) {
           nn[z] = kStale;                              // cached neighbour gone: nnd[z] stays as a lower bound
         }
+        obest = amin(obest, ArgMin{bound, z});
       }
     }
-    ybest = block_argmin(ybest, sc);   // the merged row's neighbour: min over live z of (d(y,z), z), lowest z on ties
+    // ybest: the merged row's neighbour = min over live z of (d(y,z), z), lowest z on ties; obest: min bound of the other rows
+    block_argmin2(ybest, obest, sc);
+    best = amin(obest, ArgMin{ybest.v, y});            // next step's selection
+    have_best = true;
     if (tid == 0) {
       size[x] = 0; size[y] = (uint16_t)(nx + ny);
       nn[y] = (uint16_t)ybest.i; nnd[y] = ybest.v;

@@ -385,8 +385,11 @@ __global__ void __launch_bounds__(256, 3) layernorm_rows_kernel(LnArgs a) {
 // Fast path (C % 4 == 0, which every architecture here satisfies): operand format, plane count and activation are
 // compile-time, so the per-element work is ~9 instructions and the kernel sits on the HBM roofline instead of the issue
 // limit (the generic kernel above spends ~3x that on uniform-but-dynamic branches).
-template <int NV, int FP16, int TWO, int ACT>   // ACT: 0 none, 1 GELU, 2 anything else (dispatch on a.act)
-__global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
+// A warp normalises R = 8 / NV rows per pass (one row at C = 1024, four at C = 256) so that every lane keeps eight 16-byte
+// loads in flight whatever the row length; without the layer mix the kernel fits three CTAs per SM.
+template <int NV, int FP16, int TWO, int ACT, int MIX>   // ACT: 0 none, 1 GELU, 2 anything else (dispatch on a.act)
+__global__ void __launch_bounds__(256, MIX ? 2 : 3) layernorm_rows_fast_kernel(LnArgs a) {
+  constexpr int R = 8 / NV;
   extern __shared__ float lnsm[];
   float* sg = lnsm;
   float* sb = sg + NV * 128;
@@ -399,124 +402,156 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invC = 1.0f / (float)a.C;
-  const bool mix_in = a.mix != nullptr && a.mix_src == 1, mix_out = a.mix != nullptr && a.mix_src == 2;
+  const bool mix_in = MIX && a.mix_src == 1, mix_out = MIX && a.mix_src == 2;
   const bool has_pre = a.prescale != nullptr;
   const float mw = a.mix_w;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < a.rows; row += (long long)gridDim.x * 8) {
-    const float* xr = a.x + row * a.ldx;
-    float* mr = a.mix + row * a.ldx;
-    float4 v[NV];
+  for (long long row0 = ((long long)blockIdx.x * 8 + warp) * R; row0 < a.rows; row0 += (long long)gridDim.x * 8 * R) {
+    float4 v[R][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      v[i] = (c < a.C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // rows are padded to ldx >= rup(C, 4)
-      if (c + 3 >= a.C) {   // the chunk that straddles C: the padding columns hold stale data
-        if (c + 1 >= a.C) v[i].y = 0.f;
-        if (c + 2 >= a.C) v[i].z = 0.f;
-        v[i].w = 0.f;
-      }
-    }
-    float4 m[NV];
-    if ((mix_in || mix_out) && !a.mix_init) {
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      const float* xr = a.x + row * a.ldx;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (lane + 32 * i) * 4;
-        m[i] = (c < a.C) ? *reinterpret_cast<const float4*>(mr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][i] = (c < a.C && row < a.rows) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // rows are padded to ldx >= rup(C, 4)
+        if (c + 3 >= a.C) {   // the chunk that straddles C: the padding columns hold stale data
+          if (c + 1 >= a.C) v[r][i].y = 0.f;
+          if (c + 2 >= a.C) v[r][i].z = 0.f;
+          v[r][i].w = 0.f;
+        }
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (mix_in) {
+    float4 m[MIX ? R : 1][MIX ? NV : 1];
+    if (MIX) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        m[i].x = fmaf(mw, v[i].x, m[i].x); m[i].y = fmaf(mw, v[i].y, m[i].y);
-        m[i].z = fmaf(mw, v[i].z, m[i].z); m[i].w = fmaf(mw, v[i].w, m[i].w);
-        if (c < a.C) *reinterpret_cast<float4*>(mr + c) = m[i];
+      for (int r = 0; r < R; ++r) {
+        const long long row = row0 + r;
+        float* mr = a.mix + row * a.ldx;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          m[MIX ? r : 0][MIX ? i : 0] = (!a.mix_init && c < a.C && row < a.rows) ? *reinterpret_cast<const float4*>(mr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (mix_in) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const long long row = row0 + r;
+          float* mr = a.mix + row * a.ldx;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            float4& mm = m[MIX ? r : 0][MIX ? i : 0];
+            mm.x = fmaf(mw, v[r][i].x, mm.x); mm.y = fmaf(mw, v[r][i].y, mm.y);
+            mm.z = fmaf(mw, v[r][i].z, mm.z); mm.w = fmaf(mw, v[r][i].w, mm.w);
+            if (c < a.C && row < a.rows) *reinterpret_cast<float4*>(mr + c) = mm;
+          }
+        }
       }
     }
     if (has_pre) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const float4 p4 = *reinterpret_cast<const float4*>(sp + (lane + 32 * i) * 4);
-        v[i].x *= p4.x; v[i].y *= p4.y; v[i].z *= p4.z; v[i].w *= p4.w;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { v[r][i].x *= p4.x; v[r][i].y *= p4.y; v[r][i].z *= p4.z; v[r][i].w *= p4.w; }
       }
     }
-    float s = 0.f;
+    float s[R], q[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // cells beyond C hold exact zeros
-    const float mean = warp_sum(s) * invC;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+      s[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      if (c < a.C) {
-        const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-        float4 dd = make_float4(d0, d1, d2, d3);
-        if (c + 3 >= a.C) {
-          if (c + 1 >= a.C) dd.y = 0.f;
-          if (c + 2 >= a.C) dd.z = 0.f;
-          dd.w = 0.f;
+      for (int i = 0; i < NV; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);   // cells beyond C hold exact zeros
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] = warp_sum(s[r]) * invC;                                    // mean
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      q[r] = 0.f;
+      const float mean = s[r];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < a.C) {
+          float4 dd = make_float4(v[r][i].x - mean, v[r][i].y - mean, v[r][i].z - mean, v[r][i].w - mean);
+          if (c + 3 >= a.C) {
+            if (c + 1 >= a.C) dd.y = 0.f;
+            if (c + 2 >= a.C) dd.z = 0.f;
+            dd.w = 0.f;
+          }
+          q[r] = fmaf(dd.x, dd.x, q[r]); q[r] = fmaf(dd.y, dd.y, q[r]); q[r] = fmaf(dd.z, dd.z, q[r]); q[r] = fmaf(dd.w, dd.w, q[r]);
+          v[r][i] = dd;
         }
-        q = fmaf(dd.x, dd.x, q); q = fmaf(dd.y, dd.y, q); q = fmaf(dd.z, dd.z, q); q = fmaf(dd.w, dd.w, q);
-        v[i] = dd;
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) * invC + 1e-5f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] = rsqrtf(warp_sum(q[r]) * invC + 1e-5f);                    // 1 / std
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
       const float4 g4 = *reinterpret_cast<const float4*>(sg + c);
       const float4 b4 = *reinterpret_cast<const float4*>(sb + c);
-      float4 y = make_float4(fmaf(v[i].x * rstd, g4.x, b4.x), fmaf(v[i].y * rstd, g4.y, b4.y),
-                             fmaf(v[i].z * rstd, g4.z, b4.z), fmaf(v[i].w * rstd, g4.w, b4.w));
-      if (ACT == 1) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
-      if (ACT == 2) { y.x = apply_act(y.x, a.act); y.y = apply_act(y.y, a.act); y.z = apply_act(y.z, a.act); y.w = apply_act(y.w, a.act); }
-      if (c + 3 >= a.C) {   // columns >= C (and whole chunks past C) are written as zeros
-        if (c >= a.C) y.x = 0.f;
-        if (c + 1 >= a.C) y.y = 0.f;
-        if (c + 2 >= a.C) y.z = 0.f;
-        y.w = 0.f;
-      }
-      v[i] = y;
-    }
-    if (mix_out) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        m[i].x = fmaf(mw, v[i].x, m[i].x); m[i].y = fmaf(mw, v[i].y, m[i].y);
-        m[i].z = fmaf(mw, v[i].z, m[i].z); m[i].w = fmaf(mw, v[i].w, m[i].w);
-        if (c < a.C) *reinterpret_cast<float4*>(mr + c) = m[i];
+      for (int r = 0; r < R; ++r) {
+        const float rstd = q[r];
+        float4 y = make_float4(fmaf(v[r][i].x * rstd, g4.x, b4.x), fmaf(v[r][i].y * rstd, g4.y, b4.y),
+                               fmaf(v[r][i].z * rstd, g4.z, b4.z), fmaf(v[r][i].w * rstd, g4.w, b4.w));
+        if (ACT == 1) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
+        if (ACT == 2) { y.x = apply_act(y.x, a.act); y.y = apply_act(y.y, a.act); y.z = apply_act(y.z, a.act); y.w = apply_act(y.w, a.act); }
+        if (c + 3 >= a.C) {   // columns >= C (and whole chunks past C) are written as zeros
+          if (c >= a.C) y.x = 0.f;
+          if (c + 1 >= a.C) y.y = 0.f;
+          if (c + 2 >= a.C) y.z = 0.f;
+          y.w = 0.f;
+        }
+        v[r][i] = y;
       }
     }
-    if (a.y_f32 != nullptr) {
-      float* yr = a.y_f32 + row * a.ldy;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        if (c < a.C) *reinterpret_cast<float4*>(yr + c) = v[i];
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      if (row >= a.rows) break;
+      if (mix_out) {
+        float* mr = a.mix + row * a.ldx;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          float4& mm = m[MIX ? r : 0][MIX ? i : 0];
+          mm.x = fmaf(mw, v[r][i].x, mm.x); mm.y = fmaf(mw, v[r][i].y, mm.y);
+          mm.z = fmaf(mw, v[r][i].z, mm.z); mm.w = fmaf(mw, v[r][i].w, mm.w);
+          if (c < a.C) *reinterpret_cast<float4*>(mr + c) = mm;
+        }
       }
-    }
-    if (a.y_bf != nullptr) {
-      bf16* hr = a.y_bf + row * a.ldb;
+      if (a.y_f32 != nullptr) {
+        float* yr = a.y_f32 + row * a.ldy;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        if (c + 3 < a.ldb) {  // ldb % 8 == 0: whole chunk inside the (zero padded) row
-          if (TWO) {
-            bf16 h[4], l[4];
-            split_bf16(v[i].x, h[0], l[0], FP16); split_bf16(v[i].y, h[1], l[1], FP16);
-            split_bf16(v[i].z, h[2], l[2], FP16); split_bf16(v[i].w, h[3], l[3], FP16);
-            uint2 hw, lw;
-            hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-            hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-            lw.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-            lw.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-            *reinterpret_cast<uint2*>(hr + c) = hw;
-            *reinterpret_cast<uint2*>(hr + a.bf_plane + c) = lw;
-          } else {
-            *reinterpret_cast<uint2*>(hr + c) = make_uint2(pack2_16<FP16>(v[i].x, v[i].y), pack2_16<FP16>(v[i].z, v[i].w));
+        for (int i = 0; i < NV; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          if (c < a.C) *reinterpret_cast<float4*>(yr + c) = v[r][i];
+        }
+      }
+      if (a.y_bf != nullptr) {
+        bf16* hr = a.y_bf + row * a.ldb;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (lane + 32 * i) * 4;
+          if (c + 3 < a.ldb) {  // ldb % 8 == 0: whole chunk inside the (zero padded) row
+            if (TWO) {
+              bf16 h[4], l[4];
+              split_bf16(v[r][i].x, h[0], l[0], FP16); split_bf16(v[r][i].y, h[1], l[1], FP16);
+              split_bf16(v[r][i].z, h[2], l[2], FP16); split_bf16(v[r][i].w, h[3], l[3], FP16);
+              uint2 hw, lw;
+              hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+              hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+              lw.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+              lw.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+              *reinterpret_cast<uint2*>(hr + c) = hw;
+              *reinterpret_cast<uint2*>(hr + a.bf_plane + c) = lw;
+            } else {
+              *reinterpret_cast<uint2*>(hr + c) = make_uint2(pack2_16<FP16>(v[r][i].x, v[r][i].y), pack2_16<FP16>(v[r][i].z, v[r][i].w));
+            }
           }
         }
       }
@@ -524,35 +559,40 @@ __global__ void __launch_bounds__(256, 2) layernorm_rows_fast_kernel(LnArgs a) {
   }
 }
 
-template <int NV, int FP16, int TWO>
+template <int NV, int FP16, int TWO, int MIX>
 static void launch_ln_fast(const LnArgs& a, unsigned grid, cudaStream_t st) {
   const size_t smem = 3 * NV * 128 * sizeof(float);
-  if (a.act == 0) layernorm_rows_fast_kernel<NV, FP16, TWO, 0><<<grid, 256, smem, st>>>(a);
-  else if (a.act == 1) layernorm_rows_fast_kernel<NV, FP16, TWO, 1><<<grid, 256, smem, st>>>(a);
-  else layernorm_rows_fast_kernel<NV, FP16, TWO, 2><<<grid, 256, smem, st>>>(a);
+  if (a.act == 0) layernorm_rows_fast_kernel<NV, FP16, TWO, 0, MIX><<<grid, 256, smem, st>>>(a);
+  else if (a.act == 1) layernorm_rows_fast_kernel<NV, FP16, TWO, 1, MIX><<<grid, 256, smem, st>>>(a);
+  else layernorm_rows_fast_kernel<NV, FP16, TWO, 2, MIX><<<grid, 256, smem, st>>>(a);
 }
-template <int NV>
+template <int NV, int MIX>
 static void launch_ln_fast_nv(const LnArgs& a, unsigned grid, cudaStream_t st) {
   const bool two = a.y_bf != nullptr && a.planes > 1;
-  if (a.fp16) { if (two) launch_ln_fast<NV, 1, 1>(a, grid, st); else launch_ln_fast<NV, 1, 0>(a, grid, st); }
-  else { if (two) launch_ln_fast<NV, 0, 1>(a, grid, st); else launch_ln_fast<NV, 0, 0>(a, grid, st); }
+  if (a.fp16) { if (two) launch_ln_fast<NV, 1, 1, MIX>(a, grid, st); else launch_ln_fast<NV, 1, 0, MIX>(a, grid, st); }
+  else { if (two) launch_ln_fast<NV, 0, 1, MIX>(a, grid, st); else launch_ln_fast<NV, 0, 0, MIX>(a, grid, st); }
 }
 
 cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t st) {
-  const long long want = (a.rows + 7) / 8;
-  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   static const bool generic = [] { const char* e = getenv("DZ_LN_GENERIC"); return e && e[0] == '1'; }();
   // rows must be padded to a multiple of 4 floats; with the layer mix (always D-wide, D % 4 == 0) or a ragged C the
   // chunk straddling C is masked in registers
   const bool fast = !generic && (a.ldx % 4) == 0 && a.ldx >= ((a.C + 3) & ~3) && (a.y_f32 == nullptr || (a.ldy % 4 == 0 && a.ldy >= ((a.C + 3) & ~3))) &&
                     (a.mix == nullptr || (a.C % 4) == 0);
   if (fast) {
-    if (a.C <= 256) launch_ln_fast_nv<2>(a, grid, st);
-    else if (a.C <= 512) launch_ln_fast_nv<4>(a, grid, st);
-    else if (a.C <= 1024) launch_ln_fast_nv<8>(a, grid, st);
-    else return cudaErrorInvalidValue;
+    if (a.C > 1024) return cudaErrorInvalidValue;
+    const int per_cta = 8 * (a.C <= 256 ? 4 : a.C <= 512 ? 2 : 1);                // rows per CTA pass
+    const long long want = (a.rows + per_cta - 1) / per_cta;
+    const bool mix = a.mix != nullptr;
+    const long long cap = 148 * (mix ? 2 : 3) * 4;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (a.C <= 256) { if (mix) launch_ln_fast_nv<2, 1>(a, grid, st); else launch_ln_fast_nv<2, 0>(a, grid, st); }
+    else if (a.C <= 512) { if (mix) launch_ln_fast_nv<4, 1>(a, grid, st); else launch_ln_fast_nv<4, 0>(a, grid, st); }
+    else { if (mix) launch_ln_fast_nv<8, 1>(a, grid, st); else launch_ln_fast_nv<8, 0>(a, grid, st); }
     return cudaGetLastError();
   }
+  const long long want = (a.rows + 7) / 8;
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   if (a.C <= 256) layernorm_rows_kernel<2><<<grid, 256, 3 * 2 * 128 * sizeof(float), st>>>(a);
   else if (a.C <= 512) layernorm_rows_kernel<4><<<grid, 256, 3 * 4 * 128 * sizeof(float), st>>>(a);
   else if (a.C <= 1024) layernorm_rows_kernel<8><<<grid, 256, 3 * 8 * 128 * sizeof(float), st>>>(a);
