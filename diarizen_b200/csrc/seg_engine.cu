@@ -430,7 +430,8 @@ static int plan_impl(dz_seg* s, int B, int N) {
     const float* g0 = s->conv0_gamma.as<float>(); const float* b0 = s->conv0_beta.as<float>(); const float* w0 = s->conv0_w.as<float>();
     const int C0 = c.C0, T0 = Tl[0];
     if (large) {
-      p.step("wave_stats", [s, B, N, wstats](cudaStream_t st) { return launch_wave_stats(s->cur_wav, B, N, wstats, st); });
+      void* wscratch = p.buf(wave_stats_scratch_bytes(B), true)->as<char>();
+      p.step("wave_stats", [s, B, N, wstats, wscratch](cudaStream_t st) { return launch_wave_stats(s->cur_wav, B, N, wstats, wscratch, st); });
     } else {
       p.step("conv0_moments", [s, B, N, T0, mom](cudaStream_t st) { return launch_conv0_moments(s->cur_wav, B, N, T0, mom, st); });
       p.step("conv0_gn_coef", [=](cudaStream_t st) { return launch_conv0_gn_coef(mom, w0, g0, b0, B, C0, T0, coef, st); });

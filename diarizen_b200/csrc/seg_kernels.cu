@@ -2,6 +2,7 @@
 // convolution (C_in = 1: a 10-tap stencil, HBM-bound), LayerNorm rows, the relative-position gate,
 // the conformer depthwise convolution, the classifier / log-softmax / powerset head.
 // Reference call sites are cited per kernel.
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,21 +31,52 @@ DZ_DEVINL T block_sum(T v, T* scratch /* >= 32 */) {
 // K1 waveform layer-norm statistics (large only).  reference: wav2vec2/model.py:106-113
 // stats[b] = (mean, rstd) with biased variance, eps 1e-5.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) wave_stats_kernel(const float* __restrict__ wav, int N, float* __restrict__ stats) {
+// Each window is cut into WS_SLICES slices (one CTA each, 16-byte loads, float64 sums of x and x^2); the last CTA of a window
+// to finish adds the slice sums in slice order (deterministic) and writes (mean, rstd).  scratch: [B][WS_SLICES][2] doubles
+// followed by [B] tickets (zero before the first launch; the finishing CTA resets its ticket).
+static constexpr int WS_SLICES = 16;
+__global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wav, int N, float* __restrict__ stats,
+                                                         double* __restrict__ part, unsigned* __restrict__ ticket) {
   __shared__ double sc[32];
-  const float* x = wav + (long long)blockIdx.x * N;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s += (double)x[i];
-  const double mean = block_sum<double>(s, sc) / N;
-  double q = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double dlt = (double)x[i] - mean;
-    q += dlt * dlt;
+  __shared__ unsigned s_last;
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const float* x = wav + (long long)b * N;
+  const int per = (((N + WS_SLICES - 1) / WS_SLICES) + 3) & ~3;
+  const int lo = min(N, sl * per), hi = min(N, lo + per);
+  double s = 0.0, q = 0.0;
+  if ((((uintptr_t)x) & 15) == 0) {
+    const int n4 = (hi - lo) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x + lo);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = x4[i];
+      s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    for (int i = lo + (n4 << 2) + threadIdx.x; i < hi; i += blockDim.x) { const double v = x[i]; s += v; q += v * v; }
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) { const double v = x[i]; s += v; q += v * v; }
   }
-  const double var = block_sum<double>(q, sc) / N;
+  s = block_sum<double>(s, sc);
+  q = block_sum<double>(q, sc);
   if (threadIdx.x == 0) {
-    stats[2 * blockIdx.x] = (float)mean;
-    stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    part[((long long)b * WS_SLICES + sl) * 2] = s;
+    part[((long long)b * WS_SLICES + sl) * 2 + 1] = q;
+    __threadfence();
+    s_last = atomicAdd(&ticket[b], 1u) == (unsigned)(WS_SLICES - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < WS_SLICES; ++i) {
+      ts += __ldcg(&part[((long long)b * WS_SLICES + i) * 2]);
+      tq += __ldcg(&part[((long long)b * WS_SLICES + i) * 2 + 1]);
+    }
+    const double mean = ts / N;
+    const double var = fmax(tq / N - mean * mean, 0.0);
+    stats[2 * b] = (float)mean;
+    stats[2 * b + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    ticket[b] = 0;
   }
 }
 
@@ -223,8 +255,11 @@ __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
   }
 }
 
-cudaError_t launch_wave_stats(const float* wav, int B, int N, float* stats, cudaStream_t st) {
-  wave_stats_kernel<<<B, 1024, 0, st>>>(wav, N, stats);
+size_t wave_stats_scratch_bytes(int B) { return (size_t)B * WS_SLICES * 2 * sizeof(double) + (size_t)B * sizeof(unsigned); }
+cudaError_t launch_wave_stats(const float* wav, int B, int N, float* stats, void* scratch, cudaStream_t st) {
+  double* part = reinterpret_cast<double*>(scratch);
+  unsigned* ticket = reinterpret_cast<unsigned*>(part + (size_t)B * WS_SLICES * 2);
+  wave_stats_kernel<<<dim3(WS_SLICES, B), 256, 0, st>>>(wav, N, stats, part, ticket);
   return cudaGetLastError();
 }
 cudaError_t launch_conv0_moments(const float* wav, int B, int N, int T0, double* mom, cudaStream_t st) {
@@ -639,8 +674,47 @@ __global__ void regroup_to_bf16_kernel(const float* __restrict__ x, long long ro
     if (planes > 1) out[out_plane + o] = l;
   }
 }
+// Eight columns per thread (two 16-byte loads, one 16-byte store per plane), one warp per row, one division per row: the
+// scalar kernel above pays two 64-bit divisions and 2-byte stores per element (0.36 ms for 77 M elements; this one 0.1 ms).
+__global__ void __launch_bounds__(256) regroup_to_bf16_vec8_kernel(const float* __restrict__ x, long long rows, int C, int ldx,
+                                                                   int seq_len, int seq_rows_out, int row_off, int gin, int gout,
+                                                                   bf16* __restrict__ out, long long out_plane, int ldo, int planes,
+                                                                   int fp16) {
+  const int cpr = C >> 3, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const long long sb = r / seq_len;
+    const int t = (int)(r - sb * seq_len);
+    const float* xr = x + r * ldx;
+    bf16* orow = out + (sb * seq_rows_out + t + row_off) * (long long)ldo;
+    for (int k = lane; k < cpr; k += 32) {
+      const int c = k << 3;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(xr + c)), v1 = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(v[2 * e], h0, l0, fp16);
+        split_bf16(v[2 * e + 1], h1, l1, fp16);
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      const int oc = (c / gin) * gout + (c % gin);
+      *reinterpret_cast<uint4*>(orow + oc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      if (planes > 1) *reinterpret_cast<uint4*>(orow + out_plane + oc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
 cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int seq_len, int seq_rows_out, int row_off,
                            int gin, int gout, bf16* out, long long out_plane, int ldo, int planes, int fp16, cudaStream_t st) {
+  static const bool scalar = [] { const char* e = getenv("DZ_REGROUP_SCALAR"); return e && e[0] == '1'; }();
+  if (!scalar && C % 8 == 0 && gin % 8 == 0 && gout % 8 == 0 && ldx % 4 == 0 && ldo % 8 == 0 && out_plane % 8 == 0 &&
+      (((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0) {
+    const int grid = (int)min((long long)148 * 8, (rows + 7) / 8);
+    regroup_to_bf16_vec8_kernel<<<grid, 256, 0, st>>>(x, rows, C, ldx, seq_len, seq_rows_out, row_off, gin, gout, out, out_plane,
+                                                      ldo, planes, fp16);
+    return cudaGetLastError();
+  }
   const long long total = rows * C;
   const int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   regroup_to_bf16_kernel<<<grid, 256, 0, st>>>(x, rows, C, ldx, seq_len, seq_rows_out, row_off, gin, gout, out, out_plane,
@@ -655,33 +729,59 @@ cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int s
 // first / last four rows of gru_rel_pos_linear (the reference sums the 8 outputs in two groups of 4).
 // reference: components.py:702-710.  Output layout gate[b][hi][t] (hi = index among remaining heads).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) relpos_gate_kernel(GateArgs a) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Eight lanes per head (one 16-byte load of 8 channels each), four heads per warp pass, reductions over 8 lanes.
+template <bool TWO>   // TWO: hi + lo operand planes
+__global__ void __launch_bounds__(256, TWO ? 2 : 4) relpos_gate_kernel(GateArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= a.rows) return;
   const bf16* xr = a.x + row * a.ldx;
   const long long sb = row / a.seq_len;
   const int t = (int)(row - sb * a.seq_len);
-  const float wa0 = a.wab[2 * lane], wa1 = a.wab[2 * lane + 1];
-  const float wb0 = a.wab[64 + 2 * lane], wb1 = a.wab[64 + 2 * lane + 1];
-  for (int hi = 0; hi < a.nheads; ++hi) {
-    const int h = a.head_index[hi];
-    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(xr + h * 64 + 2 * lane);
-    float x0 = from16(xv.x, a.fp16), x1 = from16(xv.y, a.fp16);
-    if (a.planes > 1) {
-      const __nv_bfloat162 xl = *reinterpret_cast<const __nv_bfloat162*>(xr + a.x_plane + h * 64 + 2 * lane);
-      x0 += from16(xl.x, a.fp16); x1 += from16(xl.y, a.fp16);
+  float wa[8], wb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wa[j] = a.wab[sub * 8 + j]; wb[j] = a.wab[64 + sub * 8 + j]; }
+  const int npass = (a.nheads + 3) >> 2;
+  uint4 raw[4], rawl[TWO ? 4 : 1];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {               // all loads of the row first (<= 16 remaining heads)
+    const int hi = it * 4 + grp;
+    raw[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (TWO) rawl[TWO ? it : 0] = raw[it];
+    if (it < npass && hi < a.nheads) {
+      const bf16* hp = xr + a.head_index[hi] * 64 + sub * 8;
+      raw[it] = *reinterpret_cast<const uint4*>(hp);
+      if (TWO) rawl[TWO ? it : 0] = *reinterpret_cast<const uint4*>(hp + a.x_plane);
     }
-    const float sa = warp_sum(wa0 * x0 + wa1 * x1) + a.ba;
-    const float sb2 = warp_sum(wb0 * x0 + wb1 * x1) + a.bb;
-    if (lane == 0) {
-      const float ga = 1.f / (1.f + expf(-sa)), gb = 1.f / (1.f + expf(-sb2));
-      a.gate[(sb * a.nheads + hi) * a.seq_len + t] = ga * (gb * a.gconst[h] - 1.f) + 2.f;
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (it >= npass) break;
+    const int hi = it * 4 + grp;
+    const bf16* e = reinterpret_cast<const bf16*>(&raw[it]);
+    const bf16* el = reinterpret_cast<const bf16*>(&rawl[TWO ? it : 0]);
+    float sa = 0.f, sb2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xv = from16(e[j], a.fp16);
+      if (TWO) xv += from16(el[j], a.fp16);
+      sa = fmaf(wa[j], xv, sa);
+      sb2 = fmaf(wb[j], xv, sb2);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb2 += __shfl_xor_sync(0xffffffffu, sb2, o);
+    }
+    if (sub == 0 && hi < a.nheads) {
+      const float ga = 1.f / (1.f + expf(-(sa + a.ba))), gb = 1.f / (1.f + expf(-(sb2 + a.bb)));
+      a.gate[(sb * a.nheads + hi) * a.seq_len + t] = ga * (gb * a.gconst[a.head_index[hi]] - 1.f) + 2.f;
     }
   }
 }
 cudaError_t launch_gate(const GateArgs& a, cudaStream_t st) {
-  relpos_gate_kernel<<<(unsigned)((a.rows + 7) / 8), 256, 0, st>>>(a);
+  if (a.planes > 1) relpos_gate_kernel<true><<<(unsigned)((a.rows + 7) / 8), 256, 0, st>>>(a);
+  else relpos_gate_kernel<false><<<(unsigned)((a.rows + 7) / 8), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -871,17 +971,23 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
   const int A = a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
   const int b = blockIdx.y, t0 = blockIdx.x * DW2_TT;
   const int nrow = DW2_TT + K - 1;
-  for (int r = 0; r < nrow; ++r) {
-    const int t = t0 + r - half;
-    const bool in = t >= 0 && t < a.T;
-    const float* xr = a.x + ((long long)b * a.T + (in ? t : 0)) * a.ldx;
-    for (int c = threadIdx.x; c < A; c += blockDim.x) {
-      float v = 0.f;
-      if (in) {
-        const float g = xr[A + c];
-        v = __fdividef(xr[c], 1.f + __expf(-g));      // GLU gate; same fast sigmoid as the GEMM epilogue's swish
+  // staging: eight rows' loads are issued before the first shared-memory store (a store per row would otherwise fence the
+  // next row's loads behind it: 94 dependent global round trips per CTA)
+  const float* __restrict__ xin = a.x;
+  for (int c = threadIdx.x; c < A; c += blockDim.x) {
+    for (int r0 = 0; r0 < nrow; r0 += 8) {
+      float xa[8], xg[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u, t = t0 + r - half;
+        const bool in = r < nrow && t >= 0 && t < a.T;
+        const float* xr = xin + ((long long)b * a.T + (in ? t : 0)) * a.ldx;
+        xa[u] = in ? __ldg(xr + c) : 0.f;
+        xg[u] = in ? __ldg(xr + A + c) : 0.f;
       }
-      smd[r * A + c] = v;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)     // GLU gate; same fast sigmoid as the GEMM epilogue's swish (rows outside the sequence: 0 / 2 = 0)
+        if (r0 + u < nrow) smd[(r0 + u) * A + c] = __fdividef(xa[u], 1.f + __expf(-xg[u]));
     }
   }
   __syncthreads();

@@ -60,7 +60,8 @@ struct HeadArgs {
   float* logp; uint8_t* multilabel;
 };
 
-cudaError_t launch_wave_stats(const float* wav, int B, int N, float* stats, cudaStream_t st);
+size_t wave_stats_scratch_bytes(int B);
+cudaError_t launch_wave_stats(const float* wav, int B, int N, float* stats, void* scratch, cudaStream_t st);   // scratch: zeroed once
 cudaError_t launch_conv0_moments(const float* wav, int B, int N, int T0, double* mom, cudaStream_t st);
 cudaError_t launch_conv0_gn_coef(const double* mom, const float* w, const float* gamma, const float* beta, int B, int C0,
                                  int T0, float* coef, cudaStream_t st);
