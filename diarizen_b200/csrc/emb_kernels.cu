@@ -3,6 +3,8 @@
 // 3x3 convolution (C_in = 1 stencil) and the masked statistics pooling (4 speaker masks per trunk output).
 // reference: pyannote-audio/pyannote/audio/models/embedding/wespeaker/__init__.py:80-103 (compute_fbank),
 //            wespeaker/resnet.py:358 (conv1 + bn1 + relu), resnet.py:49-66 + models/blocks/pooling.py:44-131 (TSTP).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "emb_kernels.h"
 
@@ -106,7 +108,203 @@ __global__ void __launch_bounds__(256) fbank_kernel(FbankArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fbank, second generation (default; DZ_FBANK_V1=1 selects the kernel above).  Same arithmetic per sample up to the
+// FFT, which is reorganised around the register file instead of shared memory:
+//  * a warp transforms TWO frames at once (frame f -> real part, frame f + 1 -> imaginary part of one complex sequence;
+//    the spectra are separated afterwards as A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i);
+//  * 512 = 8 x 8 x 8: every lane holds 16 complex points and runs two 8-point DFTs per step in registers; between the
+//    steps the points cross lanes through shared memory ONCE (two exchanges, not nine butterfly stages), with strides
+//    chosen so that every access is bank-conflict free (n = 64 n1 + 8 n2 + n3, k = k1 + 8 k2 + 64 k3:
+//    X = sum_n3 W8^{n3 k3} W512^{n3 (k1 + 8 k2)} sum_n2 W8^{n2 k2} W64^{n2 k1} sum_n1 W8^{n1 k1} x);
+//  * the per-lane twiddles of both steps are tabulated once per CTA; a CTA walks 64 frames.
+// ------------------------------------------------------------------------------------------------
+static constexpr int FB2_S = 72;        // exchange row stride (== 8 mod 32)
+static constexpr int FB2_Z = 576;       // per-warp floats per component: 8 * 72 = 576 = 512 + 4 * 16 (padded spectrum)
+static constexpr int FB2_FRAMES = 64;   // frames per CTA
+
+// in-place 8-point DFT (forward, natural order in and out)
+DZ_DEVINL void dft8(float (&r)[8], float (&i)[8]) {
+  const float h = 0.70710678118654752440f;
+  // stage 1: pairs (0,4) (2,6) (1,5) (3,7)
+  const float b0r = r[0] + r[4], b0i = i[0] + i[4], b1r = r[0] - r[4], b1i = i[0] - i[4];
+  const float b2r = r[2] + r[6], b2i = i[2] + i[6], b3r = r[2] - r[6], b3i = i[2] - i[6];
+  const float b4r = r[1] + r[5], b4i = i[1] + i[5], b5r = r[1] - r[5], b5i = i[1] - i[5];
+  const float b6r = r[3] + r[7], b6i = i[3] + i[7], b7r = r[3] - r[7], b7i = i[3] - i[7];
+  // stage 2 (-i (x + i y) = y - i x)
+  const float c0r = b0r + b2r, c0i = b0i + b2i, c2r = b0r - b2r, c2i = b0i - b2i;
+  const float c1r = b1r + b3i, c1i = b1i - b3r, c3r = b1r - b3i, c3i = b1i + b3r;
+  const float c4r = b4r + b6r, c4i = b4i + b6i, c6r = b4r - b6r, c6i = b4i - b6i;
+  const float c5r = b5r + b7i, c5i = b5i - b7r, c7r = b5r - b7i, c7i = b5i + b7r;
+  // stage 3: W8 = (1 - i) / sqrt 2, W8^2 = -i, W8^3 = (-1 - i) / sqrt 2
+  const float t5r = h * (c5r + c5i), t5i = h * (c5i - c5r);
+  const float t7r = h * (c7i - c7r), t7i = -h * (c7r + c7i);
+  r[0] = c0r + c4r; i[0] = c0i + c4i; r[4] = c0r - c4r; i[4] = c0i - c4i;
+  r[1] = c1r + t5r; i[1] = c1i + t5i; r[5] = c1r - t5r; i[5] = c1i - t5i;
+  r[2] = c2r + c6i; i[2] = c2i - c6r; r[6] = c2r - c6i; i[6] = c2i + c6r;
+  r[3] = c3r + t7r; i[3] = c3i + t7i; r[7] = c3r - t7r; i[7] = c3i - t7i;
+}
+
+__global__ void __launch_bounds__(256, 3) fbank2_kernel(FbankArgs a) {
+  extern __shared__ float smf2[];
+  float* win = smf2;                                        // [400] (416 reserved)
+  float2* tw1 = reinterpret_cast<float2*>(smf2 + 416);      // [(h * 8 + k1) * 32 + lane]  W64^{n2 k1}
+  float2* tw2 = tw1 + 512;                                  // [(h * 8 + k2) * 32 + lane]  W512^{n3 (k1 + 8 k2)}
+  float* warp_base = reinterpret_cast<float*>(tw2 + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < FB_WIN; i += blockDim.x) win[i] = a.window[i];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const int l = i & 31, j = (i >> 5) & 7, h = i >> 8;
+    const int pq = l + 32 * h;
+    const int e1 = 8 * (pq >> 3) * j;                       // W64^{n2 k1} = W512^{8 n2 k1}, n2 = p >> 3, k1 = j
+    const int e2 = (pq & 7) * ((pq >> 3) + 8 * j);          // n3 = q & 7, k1 = q >> 3, k2 = j
+    float2 t1 = a.twiddle[e1 & 255], t2 = a.twiddle[e2 & 255];
+    if (e1 & 256) { t1.x = -t1.x; t1.y = -t1.y; }
+    if (e2 & 256) { t2.x = -t2.x; t2.y = -t2.y; }
+    tw1[i] = t1; tw2[i] = t2;
+  }
+  __syncthreads();
+  float* sre = warp_base + warp * (2 * FB2_Z);
+  float* sim = sre + FB2_Z;
+  const int b = blockIdx.y;
+  const float* wav = a.wav + (long long)b * a.N;
+  const int f_end = min(a.F, (int)(blockIdx.x + 1) * FB2_FRAMES);
+  for (int f = blockIdx.x * FB2_FRAMES + 2 * warp; f < f_end; f += 16) {
+    const bool two = f + 1 < a.F;
+    // ---- the two frames: sample n = 32 s + lane in slot s (n < 400), DC removal, pre-emphasis, window
+    float zr[16], zi[16];
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr) {
+      const float* src = wav + (long long)(f + (fr && two ? 1 : 0)) * FB_HOP;
+      float x[13];
+      float sum = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 13; ++sl) {
+        const int n = 32 * sl + lane;
+        x[sl] = (n < FB_WIN) ? src[n] * 32768.0f : 0.f;
+        sum += x[sl];
+      }
+      const float mean = warp_sum(sum) / FB_WIN;
+#pragma unroll
+      for (int sl = 0; sl < 16; ++sl) {
+        float v = 0.f;
+        if (sl < 13) {
+          const int n = 32 * sl + lane;
+          const float up = __shfl_up_sync(0xffffffffu, x[sl], 1);
+          const float wrap = __shfl_sync(0xffffffffu, x[sl > 0 ? sl - 1 : 0], 31);
+          const float prev = (lane > 0) ? up : (sl > 0 ? wrap : x[0]);
+          if (n < FB_WIN) v = ((x[sl] - mean) - 0.97f * (prev - mean)) * win[n];
+        }
+        if (fr == 0) zr[sl] = v; else zi[sl] = (two ? v : 0.f);
+      }
+    }
+    // ---- step 1: DFT over n1 (slots 2 n1 + h), twiddle W64^{n2 k1}, to shared memory at [k1][p = lane + 32 h]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float r8[8], i8[8];
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) { r8[n1] = zr[2 * n1 + h]; i8[n1] = zi[2 * n1 + h]; }
+      dft8(r8, i8);
+#pragma unroll
+      for (int k1 = 0; k1 < 8; ++k1) {
+        const float2 w = tw1[(h * 8 + k1) * 32 + lane];
+        sre[k1 * FB2_S + lane + 32 * h] = r8[k1] * w.x - i8[k1] * w.y;
+        sim[k1 * FB2_S + lane + 32 * h] = r8[k1] * w.y + i8[k1] * w.x;
+      }
+    }
+    __syncwarp();
+    // ---- step 2: lane owns (k1, n3) = (q >> 3, q & 7), q = lane + 32 h: DFT over n2, twiddle W512^{n3 (k1 + 8 k2)}
+    float r2[2][8], i2[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h, base = (q >> 3) * FB2_S + (q & 7);
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) { r2[h][n2] = sre[base + n2 * 8]; i2[h][n2] = sim[base + n2 * 8]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h, base = (q >> 3) * FB2_S + (q & 7) * 9;
+      dft8(r2[h], i2[h]);
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const float2 w = tw2[(h * 8 + k2) * 32 + lane];
+        sre[base + k2] = r2[h][k2] * w.x - i2[h][k2] * w.y;
+        sim[base + k2] = r2[h][k2] * w.y + i2[h][k2] * w.x;
+      }
+    }
+    __syncwarp();
+    // ---- step 3: lane owns (k1, k2) = (r >> 3, r & 7): DFT over n3 -> Z[k1 + 8 k2 + 64 k3]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h, base = (q >> 3) * FB2_S + (q & 7);
+#pragma unroll
+      for (int n3 = 0; n3 < 8; ++n3) { r2[h][n3] = sre[base + n3 * 9]; i2[h][n3] = sim[base + n3 * 9]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+      dft8(r2[h], i2[h]);
+#pragma unroll
+      for (int k3 = 0; k3 < 8; ++k3) {
+        const int k = (q >> 3) + 8 * (q & 7) + 64 * k3;
+        sre[k + 4 * (k >> 5)] = r2[h][k3];            // padded: conflict-free here and in the reads below
+        sim[k + 4 * (k >> 5)] = i2[h][k3];
+      }
+    }
+    __syncwarp();
+    // ---- power spectra of the two frames (bins 0..256)
+    float pa[9], pb[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int k = lane + 32 * j;
+      pa[j] = 0.f; pb[j] = 0.f;
+      if (k < FB_BINS) {
+        const int kn = (FB_NFFT - k) & (FB_NFFT - 1);
+        const float zkr = sre[k + 4 * (k >> 5)], zki = sim[k + 4 * (k >> 5)];
+        const float znr = sre[kn + 4 * (kn >> 5)], zni = sim[kn + 4 * (kn >> 5)];
+        const float ar = 0.5f * (zkr + znr), ai = 0.5f * (zki - zni);
+        const float br = 0.5f * (zki + zni), bi = 0.5f * (znr - zkr);
+        pa[j] = ar * ar + ai * ai;
+        pb[j] = br * br + bi * bi;
+      }
+    }
+    __syncwarp();
+    float* PA = sre;                     // [257]
+    float* PB = sim;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int k = lane + 32 * j;
+      if (k < FB_BINS) { PA[k] = pa[j]; PB[k] = pb[j]; }
+    }
+    __syncwarp();
+    // ---- mel bins + log, mel-major output [b][mel][frame]
+    float* dst = a.out + (long long)b * 80 * a.F + f;
+    for (int m = lane; m < 80; m += 32) {
+      const int ks = a.mel_range[2 * m], ke = a.mel_range[2 * m + 1];
+      const float* wrow = a.mel_w + m * FB_BINS;
+      float acca = 0.f, accb = 0.f;
+      for (int k = ks; k < ke; ++k) {
+        const float w = __ldg(wrow + k);
+        acca = fmaf(PA[k], w, acca);
+        accb = fmaf(PB[k], w, accb);
+      }
+      dst[(long long)m * a.F] = logf(fmaxf(acca, 1.1920928955078125e-07f));
+      if (two) dst[(long long)m * a.F + 1] = logf(fmaxf(accb, 1.1920928955078125e-07f));
+    }
+    __syncwarp();
+  }
+}
+
 cudaError_t launch_fbank(const FbankArgs& a, int B, cudaStream_t st) {
+  static const bool v1 = [] { const char* e = getenv("DZ_FBANK_V1"); return e && e[0] == '1'; }();
+  if (!v1) {
+    dim3 grid2((a.F + FB2_FRAMES - 1) / FB2_FRAMES, B);
+    const size_t smem2 = sizeof(float) * (416 + 2 * 512 * 2 + 8 * 2 * FB2_Z);
+    fbank2_kernel<<<grid2, 256, smem2, st>>>(a);
+    return cudaGetLastError();
+  }
   dim3 grid((a.F + 7) / 8, B);
   const size_t smem = sizeof(float2) * (256 + 8 * FB_NFFT);
   fbank_kernel<<<grid, 256, smem, st>>>(a);

@@ -730,7 +730,7 @@ cudaError_t launch_regroup(const float* x, long long rows, int C, int ldx, int s
 // reference: components.py:702-710.  Output layout gate[b][hi][t] (hi = index among remaining heads).
 // ------------------------------------------------------------------------------------------------
 // Eight lanes per head (one 16-byte load of 8 channels each), four heads per warp pass, reductions over 8 lanes.
-template <bool TWO>   // TWO: hi + lo operand planes
+template <bool TWO, int FP16>   // TWO: hi + lo operand planes; FP16: operand format (compile-time conversions)
 __global__ void __launch_bounds__(256, TWO ? 2 : 4) relpos_gate_kernel(GateArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
   const long long row = (long long)blockIdx.x * 8 + warp;
@@ -763,8 +763,8 @@ __global__ void __launch_bounds__(256, TWO ? 2 : 4) relpos_gate_kernel(GateArgs 
     float sa = 0.f, sb2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float xv = from16(e[j], a.fp16);
-      if (TWO) xv += from16(el[j], a.fp16);
+      float xv = from16(e[j], FP16);
+      if (TWO) xv += from16(el[j], FP16);
       sa = fmaf(wa[j], xv, sa);
       sb2 = fmaf(wb[j], xv, sb2);
     }
@@ -780,8 +780,9 @@ __global__ void __launch_bounds__(256, TWO ? 2 : 4) relpos_gate_kernel(GateArgs 
   }
 }
 cudaError_t launch_gate(const GateArgs& a, cudaStream_t st) {
-  if (a.planes > 1) relpos_gate_kernel<true><<<(unsigned)((a.rows + 7) / 8), 256, 0, st>>>(a);
-  else relpos_gate_kernel<false><<<(unsigned)((a.rows + 7) / 8), 256, 0, st>>>(a);
+  const unsigned grid = (unsigned)((a.rows + 7) / 8);
+  if (a.planes > 1) { if (a.fp16) relpos_gate_kernel<true, 1><<<grid, 256, 0, st>>>(a); else relpos_gate_kernel<true, 0><<<grid, 256, 0, st>>>(a); }
+  else { if (a.fp16) relpos_gate_kernel<false, 1><<<grid, 256, 0, st>>>(a); else relpos_gate_kernel<false, 0><<<grid, 256, 0, st>>>(a); }
   return cudaGetLastError();
 }
 
@@ -965,20 +966,21 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(DwArgs a) {
 // the IEEE-division version: 264 instructions per output, most of them the two sigmoids); 64 frames per CTA (halo overhead 1.47x instead of 1.94x) and four outputs per thread in
 // flight, which share every shared-memory load (0.27 LDS per FMA instead of 1) and break the dependent FMA chain.
 static constexpr int DW2_TT = 64;
-template <int KS>   // KS > 0: kernel size known at compile time (31 in every shipped configuration) - no per-tap predicates
+template <int KS, int AA>   // KS / AA > 0: kernel size / channel count known at compile time (31 / 256 in every shipped configuration):
+                            // no per-tap predicates, shared-memory addresses are immediates (ncu: 143 -> instructions per output)
 __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
   extern __shared__ float smd[];  // [(TT + k - 1)][A]
-  const int A = a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
+  const int A = AA > 0 ? AA : a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
   const int b = blockIdx.y, t0 = blockIdx.x * DW2_TT;
   const int nrow = DW2_TT + K - 1;
-  // staging: eight rows' loads are issued before the first shared-memory store (a store per row would otherwise fence the
+  // staging: sixteen rows' loads are issued before the first shared-memory store (a store per row would otherwise fence the
   // next row's loads behind it: 94 dependent global round trips per CTA)
   const float* __restrict__ xin = a.x;
   for (int c = threadIdx.x; c < A; c += blockDim.x) {
-    for (int r0 = 0; r0 < nrow; r0 += 8) {
-      float xa[8], xg[8];
+    for (int r0 = 0; r0 < nrow; r0 += 16) {
+      float xa[16], xg[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         const int r = r0 + u, t = t0 + r - half;
         const bool in = r < nrow && t >= 0 && t < a.T;
         const float* xr = xin + ((long long)b * a.T + (in ? t : 0)) * a.ldx;
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
         xg[u] = in ? __ldg(xr + A + c) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)     // GLU gate; same fast sigmoid as the GEMM epilogue's swish (rows outside the sequence: 0 / 2 = 0)
+      for (int u = 0; u < 16; ++u)     // GLU gate; same fast sigmoid as the GEMM epilogue's swish (rows outside the sequence: 0 / 2 = 0)
         if (r0 + u < nrow) smd[(r0 + u) * A + c] = __fdividef(xa[u], 1.f + __expf(-xg[u]));
     }
   }
@@ -1035,13 +1037,15 @@ cudaError_t launch_glu_dwconv(const DwArgs& a, int B, cudaStream_t st) {
     if (smem2 <= 200 * 1024) {
       static size_t attr2 = 0;
       if (smem2 > 48 * 1024 && smem2 > attr2) {
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         attr2 = smem2;
       }
       dim3 grid2((a.T + DW2_TT - 1) / DW2_TT, B);
-      if (a.ksize == 31) glu_dwconv_v2_kernel<31><<<grid2, 256, smem2, st>>>(a);
-      else glu_dwconv_v2_kernel<0><<<grid2, 256, smem2, st>>>(a);
+      if (a.ksize == 31 && a.A == 256) glu_dwconv_v2_kernel<31, 256><<<grid2, 256, smem2, st>>>(a);
+      else if (a.ksize == 31) glu_dwconv_v2_kernel<31, 0><<<grid2, 256, smem2, st>>>(a);
+      else glu_dwconv_v2_kernel<0, 0><<<grid2, 256, smem2, st>>>(a);
       return cudaGetLastError();
     }
   }
