@@ -966,21 +966,20 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(DwArgs a) {
 // the IEEE-division version: 264 instructions per output, most of them the two sigmoids); 64 frames per CTA (halo overhead 1.47x instead of 1.94x) and four outputs per thread in
 // flight, which share every shared-memory load (0.27 LDS per FMA instead of 1) and break the dependent FMA chain.
 static constexpr int DW2_TT = 64;
-template <int KS, int AA>   // KS / AA > 0: kernel size / channel count known at compile time (31 / 256 in every shipped configuration):
-                            // no per-tap predicates, shared-memory addresses are immediates (ncu: 143 -> instructions per output)
+template <int KS>   // KS > 0: kernel size known at compile time (31 in every shipped configuration) - no per-tap predicates
 __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
   extern __shared__ float smd[];  // [(TT + k - 1)][A]
-  const int A = AA > 0 ? AA : a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
+  const int A = a.A, K = KS > 0 ? KS : a.ksize, half = (K - 1) / 2;
   const int b = blockIdx.y, t0 = blockIdx.x * DW2_TT;
   const int nrow = DW2_TT + K - 1;
-  // staging: sixteen rows' loads are issued before the first shared-memory store (a store per row would otherwise fence the
+  // staging: eight rows' loads are issued before the first shared-memory store (a store per row would otherwise fence the
   // next row's loads behind it: 94 dependent global round trips per CTA)
   const float* __restrict__ xin = a.x;
   for (int c = threadIdx.x; c < A; c += blockDim.x) {
-    for (int r0 = 0; r0 < nrow; r0 += 16) {
-      float xa[16], xg[16];
+    for (int r0 = 0; r0 < nrow; r0 += 8) {
+      float xa[8], xg[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int r = r0 + u, t = t0 + r - half;
         const bool in = r < nrow && t >= 0 && t < a.T;
         const float* xr = xin + ((long long)b * a.T + (in ? t : 0)) * a.ldx;
@@ -988,7 +987,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_v2_kernel(DwArgs a) {
         xg[u] = in ? __ldg(xr + A + c) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 16; ++u)     // GLU gate; same fast sigmoid as the GEMM epilogue's swish (rows outside the sequence: 0 / 2 = 0)
+      for (int u = 0; u < 8; ++u)     // GLU gate; same fast sigmoid as the GEMM epilogue's swish (rows outside the sequence: 0 / 2 = 0)
         if (r0 + u < nrow) smd[(r0 + u) * A + c] = __fdividef(xa[u], 1.f + __expf(-xg[u]));
     }
   }
@@ -1037,15 +1036,13 @@ cudaError_t launch_glu_dwconv(const DwArgs& a, int B, cudaStream_t st) {
     if (smem2 <= 200 * 1024) {
       static size_t attr2 = 0;
       if (smem2 > 48 * 1024 && smem2 > attr2) {
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(glu_dwconv_v2_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         attr2 = smem2;
       }
       dim3 grid2((a.T + DW2_TT - 1) / DW2_TT, B);
-      if (a.ksize == 31 && a.A == 256) glu_dwconv_v2_kernel<31, 256><<<grid2, 256, smem2, st>>>(a);
-      else if (a.ksize == 31) glu_dwconv_v2_kernel<31, 0><<<grid2, 256, smem2, st>>>(a);
-      else glu_dwconv_v2_kernel<0, 0><<<grid2, 256, smem2, st>>>(a);
+      if (a.ksize == 31) glu_dwconv_v2_kernel<31><<<grid2, 256, smem2, st>>>(a);
+      else glu_dwconv_v2_kernel<0><<<grid2, 256, smem2, st>>>(a);
       return cudaGetLastError();
     }
   }
