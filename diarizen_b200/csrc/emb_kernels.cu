@@ -380,7 +380,69 @@ __global__ void __launch_bounds__(256) emb_conv1_kernel(Conv1Args a) {
     }
   }
 }
+// Second generation (default; DZ_EMB_CONV1_V1=1 selects the kernel above).  One CTA per (window, mel) output row: the three
+// mean-subtracted input rows are staged once in shared memory; a thread owns 8 of the 32 output channels, keeps their 72
+// weights (and the folded BatchNorm) in registers for the whole row and walks the frames, so the inner loop is 9 shared-memory
+// reads + 72 FMAs per (pixel, channel group) instead of one shared-memory weight read per FMA, there is no 64-bit division per
+// pixel, and a warp's stores are 512 contiguous bytes (8 pixels x 4 channel groups x 16 B).  Same tap order per output.
+__global__ void __launch_bounds__(256, 2) emb_conv1_rows_kernel(Conv1Args a) {
+  extern __shared__ float c1rows[];   // [3][F + 2]: rows h - 1, h, h + 1 minus their means, zero border / zero outside the mel range
+  const int F = a.F, W = F + 2;
+  const int r = blockIdx.x, b = r / 80, h = r - b * 80;
+  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) {
+    const int kh = i / W, x = i - kh * W;
+    const int hh = h + kh - 1, ww = x - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < 80 && ww >= 0 && ww < F) v = a.fb[((long long)b * 80 + hh) * F + ww] - a.mean[b * 80 + hh];
+    c1rows[i] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cg = lane & 3, pl = lane >> 2;
+  float wr[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][j] = a.w[(cg * 8 + j) * 9 + t];
+    sc[j] = a.scale[cg * 8 + j];
+    sh[j] = a.shift[cg * 8 + j];
+  }
+  __syncthreads();
+  bf16* orow = a.out + ((long long)r * W + 1) * 32 + cg * 8;
+  for (int wf = warp * 8 + pl; wf < F; wf += 64) {
+    float in[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = c1rows[kh * W + wf + kw];
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = e * 2 + q;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc = fmaf(in[t], wr[t][j], acc);
+        v2[q] = fmaxf(acc * sc[j] + sh[j], 0.f);
+      }
+      bf16 h0, l0, h1, l1;
+      split_bf16(v2[0], h0, l0, a.fp16);
+      split_bf16(v2[1], h1, l1, a.fp16);
+      hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    bf16* o = orow + (long long)wf * 32;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (a.planes > 1) *reinterpret_cast<uint4*>(o + a.out_plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
 cudaError_t launch_emb_conv1(const Conv1Args& a, cudaStream_t st) {
+  static const bool v1 = [] { const char* e = getenv("DZ_EMB_CONV1_V1"); return e && e[0] == '1'; }();
+  const size_t smem = sizeof(float) * 3 * (size_t)(a.F + 2);
+  if (!v1 && smem <= 48 * 1024) {
+    emb_conv1_rows_kernel<<<a.B * 80, 256, smem, st>>>(a);
+    return cudaGetLastError();
+  }
   const long long total = (long long)a.B * 80 * a.F;
   const int grid = (int)min((long long)148 * 16, (total + 255) / 256);
   emb_conv1_kernel<<<grid, 256, 0, st>>>(a);
